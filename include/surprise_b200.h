@@ -1,0 +1,214 @@
+/*
+ * surprise_b200 -- C-ABI of the B200-native fit-time hot path of Surprise (nickmvincent/Surprise).
+ *
+ * The reference has no FFI of its own: its "operator API" for this path is (i) the module-level
+ * callables of surprise/similarities.pyx looked up by name in
+ * surprise/prediction_algorithms/algo_base.py:269-272 and (ii) the sgd()/estimate() methods of the
+ * AlgoBase subclasses in surprise/prediction_algorithms/matrix_factorization.pyx.  Every entry point
+ * below replaces one of those Cython functions and says which (file:line, relative to the reference
+ * root).  INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No torch / numpy types.
+ *   - Every function comes in two forms:
+ *       sb2_<name>_dev(...,  void* stream)  all array arguments are DEVICE pointers; work is enqueued
+ *                                           on `stream` (a cudaStream_t; NULL = default stream) and the
+ *                                           call returns after the stream has been synchronised only
+ *                                           where a status must be read back (documented per call).
+ *       sb2_<name>(...)                     all array arguments are HOST pointers; the library does
+ *                                           the H2D / D2H copies itself (this is the e2e boundary).
+ *   - Return value: SB2_OK or an error code; sb2_last_error() gives the message of the calling
+ *     thread's last failure.  There is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SB2_ERR_CUDA.
+ *   - Index types: int32 ids, int64 CSR offsets, fp64 ratings / factors at the boundary (the reference
+ *     hands Python floats / float64 ndarrays).
+ *   - "yr CSR": y_ptr[n_y+1], x_idx[nnz], r[nnz] -- the flattening of the reference's
+ *     `yr` dict-of-lists in iteration order (for y in yr: for (x, r) in yr[y]).
+ *   - "all_ratings COO": u[n], i[n], r[n] in trainset.all_ratings() order (trainset.py:180-190).
+ */
+#ifndef SURPRISE_B200_H
+#define SURPRISE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    SB2_OK = 0,
+    SB2_ERR_CUDA = 1,          /* CUDA runtime / driver failure (includes "no device") */
+    SB2_ERR_INVALID = 2,       /* bad argument */
+    SB2_ERR_ZERO_DIVISION = 3, /* the reference would raise ZeroDivisionError (cdivision=False) */
+    SB2_ERR_DUPLICATE = 4,     /* duplicate (x, y) pair in yr: not representable in the dense panels */
+    SB2_ERR_UNSUPPORTED = 5    /* ratings not representable on the exact integer-digit path */
+};
+
+enum { SB2_SIM_COSINE = 0, SB2_SIM_MSD = 1, SB2_SIM_PEARSON = 2, SB2_SIM_PEARSON_BASELINE = 3 };
+
+/* library / device introspection */
+const char* sb2_last_error(void);
+int sb2_version(void);
+int sb2_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem_bytes);
+/* kernels launched by this library on the calling thread since the last reset (bench: gpu_launches) */
+int64_t sb2_launch_count(void);
+void sb2_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Similarity matrices.  Replaces similarities.pyx:28-97 (cosine), :100-166 (msd), :169-258
+ * (pearson), :261-361 (pearson_baseline), as dispatched by algo_base.py:256-301.
+ *
+ * Ratings must be exact multiples of 1/rating_denom with r*rating_denom an integer in [0, 65535]
+ * (MovieLens stars: denom 1, half-stars: 2, Jester two-decimals: 100); they are split into base-256
+ * digits and contracted on the int8 tensor cores with exact int32 accumulation.  For cosine / msd /
+ * pearson the result is bit-identical to the reference whenever all the reference's partial sums
+ * are exactly representable (true for every integer / half-integer scale); pearson_baseline is
+ * floating point in the reference too and matches it to ~1e-12 absolute (contract: 1e-9).
+ *
+ * Rows [row_begin, row_end) of the n_x x n_x matrix are produced into sim_out (row-major,
+ * (row_end-row_begin) x n_x): the row-block shard of one rank.  row_begin = 0, row_end = n_x builds
+ * the whole matrix and exploits symmetry.  x_biases / y_biases / global_mean / shrinkage are only
+ * read for SB2_SIM_PEARSON_BASELINE (min_support is clamped to >= 2 there, similarities.pyx:334).
+ * The _dev form synchronises `stream` once to read the duplicate / zero-division status.
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx,
+                      const double* r, int64_t nnz, int rating_denom, int min_support, double global_mean,
+                      const double* x_biases, const double* y_biases, double shrinkage, int64_t row_begin,
+                      int64_t row_end, double* sim_out, void* stream);
+int sb2_sim_build(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx,
+                  const double* r, int64_t nnz, int rating_denom, int min_support, double global_mean,
+                  const double* x_biases, const double* y_biases, double shrinkage, int64_t row_begin,
+                  int64_t row_end, double* sim_out);
+
+/* Test hook: C[m x n] (int32, row-major, ld = n) = A[m x k] * B[n x k]^T for u8 operands through the
+ * tcgen05 kernel (use_tensor_cores = 1) or through the scalar dp4a cross-check kernel (0).
+ * m, n multiples of 128, k multiple of 64.  Device pointers. */
+int sb2_gemm_u8_selftest_dev(int use_tensor_cores, int64_t m, int64_t n, int64_t k, const uint8_t* a,
+                             const uint8_t* b, int32_t* c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Baselines.  Replaces prediction_algorithms/optimize_baselines.pyx:14-54 (baseline_als) and
+ * :57-84 (baseline_sgd).  ALS is bit-exact (order-preserving segmented sums); SGD is a sequential
+ * recursion and is executed as such (one thread), bit-exact but slow -- non-default in the reference.
+ * ur CSR: u_ptr[n_users+1], ui_idx[n], u_r[n] (ur[u] list order); ir CSR likewise (ir[i] list order).
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_baseline_als_dev(int64_t n_users, int64_t n_items, const int64_t* u_ptr, const int32_t* ui_idx,
+                         const double* u_r, const int64_t* i_ptr, const int32_t* iu_idx, const double* i_r,
+                         double global_mean, int n_epochs, double reg_u, double reg_i, double* bu, double* bi,
+                         void* stream);
+int sb2_baseline_als(int64_t n_users, int64_t n_items, const int64_t* u_ptr, const int32_t* ui_idx,
+                     const double* u_r, const int64_t* i_ptr, const int32_t* iu_idx, const double* i_r,
+                     double global_mean, int n_epochs, double reg_u, double reg_i, double* bu, double* bi);
+int sb2_baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                         const double* r, double global_mean, int n_epochs, double reg, double lr, double* bu,
+                         double* bi, void* stream);
+int sb2_baseline_sgd(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                     const double* r, double global_mean, int n_epochs, double reg, double lr, double* bu,
+                     double* bi);
+
+/* ------------------------------------------------------------------------------------------------
+ * SVD.  Replaces SVD.sgd, matrix_factorization.pyx:172-267 (hot loop :241-262).
+ * pu (n_users x f) and qi (n_items x f) hold the rng.normal initialisation on entry (:233-236, made
+ * on the host with numpy so that seeds agree) and the fitted factors on exit; bu / bi are outputs.
+ * `global_mean` is the trainset mean; when biased == 0 it is ignored and biases stay 0 (:238, :253).
+ * Update order is stratified (DSGD) and arithmetic is fp32: results are judged on held-out
+ * RMSE / MAE (|diff| <= 0.005), not element-wise.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sb2_sgd_params {
+    int32_t n_factors;
+    int32_t n_epochs;
+    int32_t biased;
+    int32_t reserved;
+    double global_mean;
+    double lr_bu, lr_bi, lr_pu, lr_qi, lr_yj;
+    double reg_bu, reg_bi, reg_pu, reg_qi, reg_yj;
+} sb2_sgd_params;
+
+int sb2_svd_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                    const double* r, const sb2_sgd_params* prm, double* pu, double* qi, double* bu, double* bi,
+                    void* stream);
+int sb2_svd_fit(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                const double* r, const sb2_sgd_params* prm, double* pu, double* qi, double* bu, double* bi);
+
+/* Resident-input form used by the benchmark: prepare once (stratify + upload), then run epochs with
+ * everything already in HBM.  handle lifetime: create -> (reset ->) run* -> read -> destroy. */
+typedef struct sb2_svd_plan sb2_svd_plan;
+int sb2_svd_plan_create(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u_host,
+                        const int32_t* i_host, const double* r_host, const sb2_sgd_params* prm, int with_yj,
+                        sb2_svd_plan** out);
+int sb2_svd_plan_reset(sb2_svd_plan* plan, const double* pu_host, const double* qi_host,
+                       const double* yj_host);
+int sb2_svd_plan_run(sb2_svd_plan* plan, int n_epochs, void* stream); /* async on stream */
+int sb2_svd_plan_read(sb2_svd_plan* plan, double* pu, double* qi, double* bu, double* bi, double* yj);
+void sb2_svd_plan_destroy(sb2_svd_plan* plan);
+/* algorithmic bytes per rating update of the plan's kernel (2*(2f+2)*4 + 12 for SVD) */
+int64_t sb2_svd_plan_bytes_per_update(const sb2_svd_plan* plan);
+int sb2_svd_plan_grid(const sb2_svd_plan* plan, int* n_blocks, int* n_sub);
+
+/* SVD++.  Replaces SVDpp.sgd, matrix_factorization.pyx:420-504.  yj (n_items x f) in/out like qi.
+ * u_ptr / ui_idx: the ur CSR (I_u).  See DESIGN.md for the per-user batching of the y_j update. */
+int sb2_svdpp_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                      const double* r, const int64_t* u_ptr, const int32_t* ui_idx, const sb2_sgd_params* prm,
+                      double* pu, double* qi, double* yj, double* bu, double* bi, void* stream);
+int sb2_svdpp_fit(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                  const double* r, const int64_t* u_ptr, const int32_t* ui_idx, const sb2_sgd_params* prm,
+                  double* pu, double* qi, double* yj, double* bu, double* bi);
+
+/* ------------------------------------------------------------------------------------------------
+ * NMF.  Replaces NMF.sgd, matrix_factorization.pyx:646-735.  Bit-exact (fp64, the reference's
+ * summation order, no FMA) for biased == 0 and biased != 0.  (u, i, r) is the all_ratings COO, which
+ * must be grouped by u (it is, by construction of all_ratings()).  pu / qi: rng.uniform init in,
+ * factors out.  Returns SB2_ERR_ZERO_DIVISION where the reference raises (:723, :730).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sb2_nmf_params {
+    int32_t n_factors;
+    int32_t n_epochs;
+    int32_t biased;
+    int32_t reserved;
+    double global_mean;
+    double reg_pu, reg_qi, reg_bu, reg_bi, lr_bu, lr_bi;
+} sb2_nmf_params;
+
+int sb2_nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                    const double* r, const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi,
+                    void* stream);
+int sb2_nmf_fit(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                const double* r, const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched estimate for the factor models.  Replaces SVD.estimate (matrix_factorization.pyx:269-299),
+ * NMF.estimate (:737-761) and SVDpp.estimate (:506-522; yj != NULL) called once per pair by
+ * AlgoBase.test (algo_base.py:191-218).  u[k] < 0 / i[k] < 0 encode an unknown user / item.
+ * impossible[k] = 1 where the reference raises PredictionImpossible.
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_mf_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int n_factors, int biased,
+                       double global_mean, const double* pu, const double* qi, const double* bu,
+                       const double* bi, const double* yj, const int64_t* u_ptr, const int32_t* ui_idx,
+                       double* est, uint8_t* impossible, void* stream);
+int sb2_mf_predict(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t n_users, int64_t n_items,
+                   int n_factors, int biased, double global_mean, const double* pu, const double* qi,
+                   const double* bu, const double* bi, const double* yj, const int64_t* u_ptr,
+                   const int32_t* ui_idx, double* est, uint8_t* impossible);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched k-NN estimate.  Replaces KNNBasic.estimate (knns.py:99-123) and KNNBaseline.estimate
+ * (:274-309): gather sim[x, x2] over yr[y], stable top-k (heapq.nlargest semantics), ordered fp64
+ * weighted sum -- bit-identical to the reference.
+ * mode: 0 = KNNBasic; 1 = KNNBaseline with x = user (user_based); 2 = KNNBaseline with x = item.
+ * x[k] / y[k] < 0 = unknown.  actual_k[k] = -1 where the reference reports no actual_k.
+ * impossible[k]: 1 = PredictionImpossible, 2 = the reference would raise ZeroDivisionError.
+ * sim: n_x x n_x row-major with leading dimension sim_ld (>= n_x).
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_knn_predict_dev(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t n_x, const double* sim,
+                        int64_t sim_ld, const int64_t* y_ptr, const int32_t* x_idx, const double* r, int k,
+                        int min_k, int mode, double global_mean, const double* bx, const double* by,
+                        double* est, int32_t* actual_k, uint8_t* impossible, void* stream);
+int sb2_knn_predict(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t n_x, int64_t n_y,
+                    const double* sim, const int64_t* y_ptr, const int32_t* x_idx, const double* r, int k,
+                    int min_k, int mode, double global_mean, const double* bx, const double* by, double* est,
+                    int32_t* actual_k, uint8_t* impossible);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURPRISE_B200_H */

@@ -1,0 +1,185 @@
+// Batched estimate kernels: factor models (gather + dot) and k-NN (gather + stable top-k select +
+// ordered weighted sum).  These replace the per-pair Python estimate() calls that AlgoBase.test makes
+// (algo_base.py:191-218 -> matrix_factorization.pyx:269-299 / :506-522 / :737-761, knns.py:99-123 /
+// :274-309).
+#include "common.cuh"
+
+namespace sb2 {
+
+// ------------------------------------------------------------------------------------------------
+// Factor models.  One warp per (u, i) pair; lanes stride the factor dimension, partial dots are
+// combined with a shuffle tree (the reference uses np.dot, whose summation order is BLAS-defined, so
+// the contract here is fp64 accuracy, not bit equality).
+// ------------------------------------------------------------------------------------------------
+__global__ void mf_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int f,
+                                  int biased, double mu, const double* __restrict__ pu, const double* __restrict__ qi,
+                                  const double* __restrict__ bu, const double* __restrict__ bi,
+                                  const double* __restrict__ yj, const int64_t* __restrict__ u_ptr,
+                                  const int32_t* __restrict__ ui_idx, double* __restrict__ est,
+                                  uint8_t* __restrict__ impossible) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_pairs) return;
+    const int32_t uu = u[k], ii = i[k];
+    const bool ku = uu >= 0, ki = ii >= 0;
+    double e = 0.0;
+    uint8_t imp = 0;
+    if (biased) {
+        e = mu;
+        if (ku) e += bu[uu];
+        if (ki) e += bi[ii];
+    } else if (!(ku && ki)) {
+        imp = 1;  // PredictionImpossible('User and item are unkown.')
+    }
+    if (ku && ki) {
+        const double* p = pu + (size_t)uu * f;
+        const double* q = qi + (size_t)ii * f;
+        double part = 0.0;
+        if (yj) {
+            const int64_t b = u_ptr[uu], en = u_ptr[uu + 1];
+            const double sq = sqrt((double)(en - b));
+            for (int j = lane; j < f; j += 32) {
+                double s = 0.0;
+                for (int64_t a = b; a < en; ++a) s += yj[(size_t)ui_idx[a] * f + j];
+                part += q[j] * (p[j] + s / sq);
+            }
+        } else {
+            for (int j = lane; j < f; j += 32) part += q[j] * p[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        e = biased ? e + part : part;
+    }
+    if (lane == 0) {
+        est[k] = e;
+        impossible[k] = imp;
+    }
+}
+
+int mf_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int f, int biased, double mu, const double* pu,
+                   const double* qi, const double* bu, const double* bi, const double* yj, const int64_t* u_ptr,
+                   const int32_t* ui_idx, double* est, uint8_t* impossible, cudaStream_t st) {
+    if (n_pairs <= 0) return SB2_OK;
+    const int threads = 256;
+    mf_predict_kernel<<<(unsigned)ceil_div(n_pairs * 32, threads), threads, 0, st>>>(
+        n_pairs, u, i, f, biased, mu, pu, qi, bu, bi, yj, u_ptr, ui_idx, est, impossible);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-NN.  One warp per (x, y) pair.
+//   neighbors = [(sim[x, x2], r) for (x2, r) in yr[y]]; heapq.nlargest(k, key=sim)
+// heapq.nlargest == sorted(reverse=True)[:k]: descending by sim, ties keep list order.  The warp
+// repeats k rounds of "smallest element after the previously selected one in the total order
+// (sim desc, position asc)" with a shuffle arg-max; the gathered sims live in shared memory when the
+// list fits, otherwise they are re-gathered from the sim row.  The weighted sums are accumulated by
+// every lane identically, in selection order, in round-to-nearest fp64 without contraction -- the
+// same sequence of operations as the reference, hence the same bits.
+// ------------------------------------------------------------------------------------------------
+constexpr int KNN_WARPS = 8;
+constexpr int KNN_CACHE = 768;  // sims cached per warp (doubles)
+
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t* __restrict__ y, int64_t n_x,
+                   const double* __restrict__ sim, int64_t sim_ld, const int64_t* __restrict__ y_ptr,
+                   const int32_t* __restrict__ x_idx, const double* __restrict__ r, int k, int min_k, int mode,
+                   double mu, const double* __restrict__ bx, const double* __restrict__ by, double* __restrict__ est,
+                   int32_t* __restrict__ actual_k, uint8_t* __restrict__ impossible) {
+    __shared__ double cache[KNN_WARPS][KNN_CACHE];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t p = blockIdx.x * (int64_t)KNN_WARPS + w; p < n_pairs; p += (int64_t)gridDim.x * KNN_WARPS) {
+        const int32_t xx = x[p], yy = y[p];
+        const bool kx = xx >= 0, ky = yy >= 0;
+        double e = 0.0;
+        int ak = -1;
+        uint8_t imp = 0;
+        if (mode != 0) {
+            e = mu;
+            // est += bu[u] first, then bi[i] (knns.py:276-280); mode 1: x is the user, mode 2: y is
+            if (mode == 1) { if (kx) e = __dadd_rn(e, bx[xx]); if (ky) e = __dadd_rn(e, by[yy]); }
+            else { if (ky) e = __dadd_rn(e, by[yy]); if (kx) e = __dadd_rn(e, bx[xx]); }
+        }
+        if (!(kx && ky)) {
+            if (mode == 0) imp = 1;
+        } else {
+            const int64_t b = y_ptr[yy], len = y_ptr[yy + 1] - b;
+            const double* srow = sim + (size_t)xx * (size_t)sim_ld;
+            const bool cached = len <= KNN_CACHE;
+            if (cached) {
+                for (int64_t a = lane; a < len; a += 32) cache[w][a] = srow[x_idx[b + a]];
+                __syncwarp();
+            }
+            double last_s = 0.0;
+            int64_t last_pos = -1;
+            bool first = true;
+            double sum_sim = 0.0, sum_r = 0.0;
+            ak = 0;
+            const int64_t rounds = len < (int64_t)k ? len : (int64_t)k;
+            for (int64_t t = 0; t < rounds; ++t) {
+                // best candidate strictly after (last_s, last_pos) in (sim desc, pos asc) order
+                double bs = 0.0;
+                int64_t bp = -1;
+                for (int64_t a = lane; a < len; a += 32) {
+                    const double s = cached ? cache[w][a] : srow[x_idx[b + a]];
+                    const bool after = first || s < last_s || (s == last_s && a > last_pos);
+                    if (after && (bp < 0 || s > bs)) { bs = s; bp = a; }  // ascending a: first max wins
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double os = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
+                    const int64_t op = __shfl_xor_sync(0xFFFFFFFFu, bp, o);
+                    if (op >= 0 && (bp < 0 || os > bs || (os == bs && op < bp))) { bs = os; bp = op; }
+                }
+                if (bp < 0) break;  // only NaNs left
+                first = false;
+                last_s = bs;
+                last_pos = bp;
+                if (!(bs > 0.0)) break;  // everything that follows is <= 0 and contributes nothing
+                const double rr = r[b + bp];
+                sum_sim = __dadd_rn(sum_sim, bs);
+                if (mode != 0) {
+                    const double nb_bsl = __dadd_rn(__dadd_rn(mu, bx[x_idx[b + bp]]), by[yy]);
+                    sum_r = __dadd_rn(sum_r, __dmul_rn(bs, __dsub_rn(rr, nb_bsl)));
+                } else {
+                    sum_r = __dadd_rn(sum_r, __dmul_rn(bs, rr));
+                }
+                ++ak;
+            }
+            if (mode != 0) {
+                if (ak < min_k) sum_r = 0.0;
+                if (ak > 0) e = __dadd_rn(e, __ddiv_rn(sum_r, sum_sim));  // ZeroDivisionError swallowed otherwise
+            } else {
+                if (ak < min_k) imp = 1;       // PredictionImpossible('Not enough neighbors.')
+                else if (ak == 0) imp = 2;     // min_k <= 0: the reference divides 0 / 0
+                else e = __ddiv_rn(sum_r, sum_sim);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            est[p] = e;
+            actual_k[p] = ak;
+            impossible[p] = imp;
+        }
+    }
+}
+
+int knn_predict_dev(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t n_x, const double* sim,
+                    int64_t sim_ld, const int64_t* y_ptr, const int32_t* x_idx, const double* r, int k, int min_k,
+                    int mode, double mu, const double* bx, const double* by, double* est, int32_t* actual_k,
+                    uint8_t* impossible, cudaStream_t st) {
+    if (n_pairs <= 0) return SB2_OK;
+    if (mode < 0 || mode > 2 || (mode != 0 && (!bx || !by))) {
+        set_error("knn_predict: invalid mode / missing baselines");
+        return SB2_ERR_INVALID;
+    }
+    int64_t blocks = ceil_div(n_pairs, KNN_WARPS);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    knn_predict_kernel<<<(unsigned)blocks, KNN_WARPS * 32, 0, st>>>(n_pairs, x, y, n_x, sim, sim_ld, y_ptr, x_idx, r, k,
+                                                                    min_k, mode, mu, bx, by, est, actual_k, impossible);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+}  // namespace sb2

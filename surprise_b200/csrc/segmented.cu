@@ -1,0 +1,361 @@
+// Order-preserving segmented kernels: baselines (ALS / SGD) and NMF.
+//
+// Bit-exactness discipline: the reference is strict IEEE fp64 without FMA contraction and with a
+// fixed summation order, so every accumulation below is a *sequential* chain of __dadd_rn /
+// __dmul_rn / __ddiv_rn in the reference's order; parallelism is across segments (users, items) and
+// across factors, never inside one ordered sum.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace sb2 {
+
+enum { SEG_ZERODIV = 0 };
+
+// =================================================================================================
+// baseline_als  (optimize_baselines.pyx:14-54)
+//   bi[i] = (sum_{(u,r) in ir[i]} r - mu - bu[u]) / (reg_i + |ir[i]|)   then the same for users.
+// One thread per segment walks its list in order.
+// =================================================================================================
+__global__ void als_pass_kernel(int64_t n_seg, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                const double* __restrict__ r, const double* other, double* mine, double mu,
+                                double reg, int* status) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const int64_t b = ptr[s], e = ptr[s + 1];
+    double dev = 0.0;
+    for (int64_t a = b; a < e; ++a) dev = __dadd_rn(dev, __dsub_rn(__dsub_rn(r[a], mu), other[idx[a]]));
+    const double den = __dadd_rn(reg, (double)(e - b));
+    if (den == 0.0) {
+        atomicExch(&status[SEG_ZERODIV], 1);
+        return;
+    }
+    mine[s] = __ddiv_rn(dev, den);
+}
+
+int baseline_als_dev(int64_t n_users, int64_t n_items, const int64_t* u_ptr, const int32_t* ui_idx, const double* u_r,
+                     const int64_t* i_ptr, const int32_t* iu_idx, const double* i_r, double mu, int n_epochs,
+                     double reg_u, double reg_i, double* bu, double* bi, cudaStream_t st) {
+    DevBuf status;
+    SB2_TRY(status.alloc(sizeof(int), st));
+    SB2_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), st));
+    SB2_CUDA(cudaMemsetAsync(bu, 0, (size_t)n_users * sizeof(double), st));
+    SB2_CUDA(cudaMemsetAsync(bi, 0, (size_t)n_items * sizeof(double), st));
+    for (int ep = 0; ep < n_epochs; ++ep) {
+        if (n_items > 0) {
+            als_pass_kernel<<<(unsigned)ceil_div(n_items, 128), 128, 0, st>>>(n_items, i_ptr, iu_idx, i_r, bu, bi, mu,
+                                                                              reg_i, status.as<int>());
+            SB2_LAUNCH_CHECK();
+        }
+        if (n_users > 0) {
+            als_pass_kernel<<<(unsigned)ceil_div(n_users, 128), 128, 0, st>>>(n_users, u_ptr, ui_idx, u_r, bi, bu, mu,
+                                                                              reg_u, status.as<int>());
+            SB2_LAUNCH_CHECK();
+        }
+    }
+    int h = 0;
+    SB2_CUDA(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    if (h) {
+        set_error("float division");
+        return SB2_ERR_ZERO_DIVISION;
+    }
+    return SB2_OK;
+}
+
+// baseline_sgd (optimize_baselines.pyx:57-84): a sequential recursion through bu/bi over
+// all_ratings() -- executed as such by one thread (bit-exact; the reference's non-default method).
+__global__ void baseline_sgd_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i,
+                                    const double* __restrict__ r, double mu, int n_epochs, double reg, double lr,
+                                    double* bu, double* bi) {
+    if (blockIdx.x || threadIdx.x) return;
+    for (int ep = 0; ep < n_epochs; ++ep)
+        for (int64_t k = 0; k < n; ++k) {
+            const int32_t uu = u[k], ii = i[k];
+            const double b_u = bu[uu], b_i = bi[ii];
+            const double err = __dsub_rn(r[k], __dadd_rn(__dadd_rn(mu, b_u), b_i));
+            bu[uu] = __dadd_rn(b_u, __dmul_rn(lr, __dsub_rn(err, __dmul_rn(reg, b_u))));
+            bi[ii] = __dadd_rn(b_i, __dmul_rn(lr, __dsub_rn(err, __dmul_rn(reg, b_i))));
+        }
+}
+
+int baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
+                     double mu, int n_epochs, double reg, double lr, double* bu, double* bi, cudaStream_t st) {
+    SB2_CUDA(cudaMemsetAsync(bu, 0, (size_t)n_users * sizeof(double), st));
+    SB2_CUDA(cudaMemsetAsync(bi, 0, (size_t)n_items * sizeof(double), st));
+    baseline_sgd_kernel<<<1, 32, 0, st>>>(n, u, i, r, mu, n_epochs, reg, lr, bu, bi);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+// =================================================================================================
+// NMF  (matrix_factorization.pyx:684-730)
+//
+// Per epoch the reference makes one pass over all_ratings() accumulating, for every rating k=(u,i,r):
+//   est_k = mu + bu[u] + bi[i] + sum_f qi[i,f]*pu[u,f]            (f ascending, mul then add)
+//   user_num[u,f] += qi[i,f]*r      user_denom[u,f] += qi[i,f]*est_k
+//   item_num[i,f] += pu[u,f]*r      item_denom[i,f] += pu[u,f]*est_k
+// then  pu[u,f] *= user_num / (user_denom + |ur[u]|*reg_pu*pu[u,f])  and the same for items, both
+// from the OLD pu / qi (the accumulators were built before either update).
+//
+// Each accumulator element is an ordered sum over one user's (one item's) ratings in all_ratings()
+// order.  A group of G = 2^ceil(log2 f) (<= 32) lanes owns one segment; lane l owns factors
+// l, l+G, ...  The dot product for est_k is recomputed inside both passes by chaining the per-factor
+// products in factor order through warp shuffles, so every lane obtains the bit-identical est_k and no
+// N-sized est array ever travels through HBM (unbiased model).  The biased model makes bu/bi a
+// sequential recursion over all ratings (:707-709); that part runs on one thread and hands est_k to
+// the two passes through an array.
+// =================================================================================================
+template <int G>
+__device__ __forceinline__ double ordered_dot(const double* __restrict__ prow, const double* __restrict__ qrow, int f,
+                                              int gl, unsigned gmask, int gbase) {
+    // all lanes of the group return sum_{j<f} q[j]*p[j] accumulated in index order
+    double dot = 0.0;
+    for (int j0 = 0; j0 < f; j0 += G) {
+        const int j = j0 + gl;
+        const double prod = (j < f) ? __dmul_rn(qrow[j], prow[j]) : 0.0;
+        const int lim = min(G, f - j0);
+        for (int l = 0; l < lim; ++l) dot = __dadd_rn(dot, __shfl_sync(gmask, prod, gbase + l));
+    }
+    return dot;
+}
+
+// One pass: segments are users (side = 0: fixed row = pu[u], gathered rows = qi[i_a]) or items (side = 1).
+// seg_ptr/other_idx/r_seg: CSR of the side in all_ratings() order; est_seg: optional est per entry.
+template <int G>
+__global__ void nmf_pass_kernel(int64_t n_seg, int f, const int64_t* __restrict__ seg_ptr,
+                                const int32_t* __restrict__ other_idx, const double* __restrict__ r_seg,
+                                const double* __restrict__ est_seg, const double* __restrict__ mine_old,
+                                const double* __restrict__ other_old, double* __restrict__ mine_new, double reg,
+                                int* status) {
+    const int gpb = blockDim.x / G;
+    const int gl = threadIdx.x % G;
+    const int gbase = (threadIdx.x % 32) / G * G;
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gbase);
+    const int64_t seg = blockIdx.x * (int64_t)gpb + threadIdx.x / G;
+    if (seg >= n_seg) return;  // whole groups exit together
+    const int64_t b = seg_ptr[seg], e = seg_ptr[seg + 1];
+    const double* myrow = mine_old + (size_t)seg * f;
+    constexpr int MAXS = 8;  // factors per lane: f <= 32*8
+    double num[MAXS], den[MAXS];
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s) num[s] = den[s] = 0.0;
+    for (int64_t a = b; a < e; ++a) {
+        const double* orow = other_old + (size_t)other_idx[a] * f;
+        const double r = r_seg[a];
+        double est;
+        if (est_seg) est = est_seg[a];
+        else est = ordered_dot<G>(myrow, orow, f, gl, gmask, gbase);  // mu = bu = bi = 0: est == dot
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) {
+            const int j = gl + s * G;
+            if (j < f) {
+                const double o = orow[j];
+                num[s] = __dadd_rn(num[s], __dmul_rn(o, r));
+                den[s] = __dadd_rn(den[s], __dmul_rn(o, est));
+            }
+        }
+    }
+    const double nr = (double)(e - b);
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s) {
+        const int j = gl + s * G;
+        if (j < f) {
+            const double p = myrow[j];
+            const double d = __dadd_rn(den[s], __dmul_rn(__dmul_rn(nr, reg), p));
+            if (d == 0.0) atomicExch(&status[SEG_ZERODIV], 1);
+            mine_new[(size_t)seg * f + j] = __dmul_rn(p, __ddiv_rn(num[s], d));
+        }
+    }
+}
+
+// biased model: sequential bias recursion + est per rating (all_ratings order), one thread.
+__global__ void nmf_dot_kernel(int64_t n, int f, const int32_t* __restrict__ u, const int32_t* __restrict__ i,
+                               const double* __restrict__ pu, const double* __restrict__ qi, double* __restrict__ dot) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* p = pu + (size_t)u[k] * f;
+    const double* q = qi + (size_t)i[k] * f;
+    double d = 0.0;
+    for (int j = 0; j < f; ++j) d = __dadd_rn(d, __dmul_rn(q[j], p[j]));
+    dot[k] = d;
+}
+
+__global__ void nmf_bias_scan_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i,
+                                     const double* __restrict__ r, const double* __restrict__ dot, double mu,
+                                     double lr_bu, double lr_bi, double reg_bu, double reg_bi, double* bu, double* bi,
+                                     double* __restrict__ est) {
+    if (blockIdx.x || threadIdx.x) return;
+    for (int64_t k = 0; k < n; ++k) {
+        const int32_t uu = u[k], ii = i[k];
+        const double b_u = bu[uu], b_i = bi[ii];
+        const double e = __dadd_rn(__dadd_rn(__dadd_rn(mu, b_u), b_i), dot[k]);
+        est[k] = e;
+        const double err = __dsub_rn(r[k], e);
+        bu[uu] = __dadd_rn(b_u, __dmul_rn(lr_bu, __dsub_rn(err, __dmul_rn(reg_bu, b_u))));
+        bi[ii] = __dadd_rn(b_i, __dmul_rn(lr_bi, __dsub_rn(err, __dmul_rn(reg_bi, b_i))));
+    }
+}
+
+__global__ void iota_kernel(int64_t n, int64_t* v) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) v[k] = k;
+}
+__global__ void count_kernel(int64_t n, const int32_t* __restrict__ key, unsigned long long* cnt) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) atomicAdd(&cnt[key[k]], 1ull);
+}
+__global__ void gather_item_side_kernel(int64_t n, const int64_t* __restrict__ perm, const int32_t* __restrict__ u,
+                                        const double* __restrict__ r, int32_t* __restrict__ u_out,
+                                        double* __restrict__ r_out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) {
+        u_out[k] = u[perm[k]];
+        r_out[k] = r[perm[k]];
+    }
+}
+__global__ void gather_f64_kernel(int64_t n, const int64_t* __restrict__ perm, const double* __restrict__ src,
+                                  double* __restrict__ dst) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) dst[k] = src[perm[k]];
+}
+__global__ void check_grouped_kernel(int64_t n, const int32_t* __restrict__ u, int* status) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k + 1 < n && u[k + 1] < u[k]) atomicExch(&status[1], 1);
+}
+
+template <int G>
+static int launch_pass(int64_t n_seg, int f, const int64_t* ptr, const int32_t* idx, const double* r, const double* est,
+                       const double* mine_old, const double* other_old, double* mine_new, double reg, int* status,
+                       cudaStream_t st) {
+    const int threads = 128, gpb = threads / G;
+    nmf_pass_kernel<G><<<(unsigned)ceil_div(n_seg, gpb), threads, 0, st>>>(n_seg, f, ptr, idx, r, est, mine_old,
+                                                                           other_old, mine_new, reg, status);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+static int nmf_pass(int64_t n_seg, int f, const int64_t* ptr, const int32_t* idx, const double* r, const double* est,
+                    const double* mine_old, const double* other_old, double* mine_new, double reg, int* status,
+                    cudaStream_t st) {
+    if (n_seg <= 0) return SB2_OK;
+    if (f <= 4) return launch_pass<4>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
+    if (f <= 8) return launch_pass<8>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
+    if (f <= 16) return launch_pass<16>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
+    return launch_pass<32>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
+}
+
+int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
+                const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi, cudaStream_t st) {
+    const int f = prm->n_factors;
+    if (f <= 0 || f > 256 || n_users <= 0 || n_items <= 0 || n < 0) {
+        set_error("nmf_fit: invalid shape (n_factors must be in [1, 256])");
+        return SB2_ERR_INVALID;
+    }
+    const bool biased = prm->biased != 0;
+    const double mu = biased ? prm->global_mean : 0.0;
+
+    DevBuf status_d, cnt_u, cnt_i, ptr_u, ptr_i, perm, perm_in, keys_out, u_it, r_it, pu2, qi2, tmp, dot_d, est_d, est_it;
+    SB2_TRY(status_d.alloc(2 * sizeof(int), st));
+    SB2_CUDA(cudaMemsetAsync(status_d.p, 0, 2 * sizeof(int), st));
+    SB2_CUDA(cudaMemsetAsync(bu, 0, (size_t)n_users * sizeof(double), st));
+    SB2_CUDA(cudaMemsetAsync(bi, 0, (size_t)n_items * sizeof(double), st));
+    const unsigned nb = (unsigned)ceil_div(std::max<int64_t>(n, 1), 256);
+
+    // user CSR = the COO itself (grouped by u); item CSC = stable sort of positions by item
+    SB2_TRY(cnt_u.alloc((size_t)(n_users + 1) * 8, st));
+    SB2_TRY(cnt_i.alloc((size_t)(n_items + 1) * 8, st));
+    SB2_TRY(ptr_u.alloc((size_t)(n_users + 1) * 8, st));
+    SB2_TRY(ptr_i.alloc((size_t)(n_items + 1) * 8, st));
+    SB2_CUDA(cudaMemsetAsync(cnt_u.p, 0, (size_t)(n_users + 1) * 8, st));
+    SB2_CUDA(cudaMemsetAsync(cnt_i.p, 0, (size_t)(n_items + 1) * 8, st));
+    if (n > 0) {
+        check_grouped_kernel<<<nb, 256, 0, st>>>(n, u, status_d.as<int>());
+        SB2_LAUNCH_CHECK();
+        count_kernel<<<nb, 256, 0, st>>>(n, u, cnt_u.as<unsigned long long>());
+        SB2_LAUNCH_CHECK();
+        count_kernel<<<nb, 256, 0, st>>>(n, i, cnt_i.as<unsigned long long>());
+        SB2_LAUNCH_CHECK();
+    }
+    {
+        size_t tb1 = 0, tb2 = 0, tb3 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb1, cnt_u.as<int64_t>(), ptr_u.as<int64_t>(), (int)(n_users + 1), st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt_i.as<int64_t>(), ptr_i.as<int64_t>(), (int)(n_items + 1), st);
+        SB2_TRY(perm.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+        SB2_TRY(perm_in.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+        SB2_TRY(keys_out.alloc((size_t)std::max<int64_t>(n, 1) * 4, st));
+        cub::DeviceRadixSort::SortPairs(nullptr, tb3, i, keys_out.as<int32_t>(), perm_in.as<int64_t>(),
+                                        perm.as<int64_t>(), (int)n, 0, 32, st);
+        size_t tb = std::max(tb1, std::max(tb2, tb3));
+        SB2_TRY(tmp.alloc(tb + 16, st));
+        SB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_u.as<int64_t>(), ptr_u.as<int64_t>(), (int)(n_users + 1), st));
+        SB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_i.as<int64_t>(), ptr_i.as<int64_t>(), (int)(n_items + 1), st));
+        sb2::launch_counter() += 2;
+        if (n > 0) {
+            iota_kernel<<<nb, 256, 0, st>>>(n, perm_in.as<int64_t>());
+            SB2_LAUNCH_CHECK();
+            // LSD radix sort is stable: equal items keep all_ratings() order (u ascending, then ur[u] order)
+            SB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, i, keys_out.as<int32_t>(), perm_in.as<int64_t>(),
+                                                     perm.as<int64_t>(), (int)n, 0, 32, st));
+            sb2::launch_counter() += 1;
+        }
+    }
+    SB2_TRY(u_it.alloc((size_t)std::max<int64_t>(n, 1) * 4, st));
+    SB2_TRY(r_it.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+    if (n > 0) {
+        gather_item_side_kernel<<<nb, 256, 0, st>>>(n, perm.as<int64_t>(), u, r, u_it.as<int32_t>(), r_it.as<double>());
+        SB2_LAUNCH_CHECK();
+    }
+    SB2_TRY(pu2.alloc((size_t)n_users * f * 8, st));
+    SB2_TRY(qi2.alloc((size_t)n_items * f * 8, st));
+    if (biased) {
+        SB2_TRY(dot_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+        SB2_TRY(est_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+        SB2_TRY(est_it.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+    }
+
+    double* pu_cur = pu;
+    double* pu_nxt = pu2.as<double>();
+    double* qi_cur = qi;
+    double* qi_nxt = qi2.as<double>();
+    for (int ep = 0; ep < prm->n_epochs; ++ep) {
+        const double* est_u = nullptr;
+        const double* est_i = nullptr;
+        if (biased && n > 0) {
+            nmf_dot_kernel<<<nb, 256, 0, st>>>(n, f, u, i, pu_cur, qi_cur, dot_d.as<double>());
+            SB2_LAUNCH_CHECK();
+            nmf_bias_scan_kernel<<<1, 32, 0, st>>>(n, u, i, r, dot_d.as<double>(), mu, prm->lr_bu, prm->lr_bi,
+                                                   prm->reg_bu, prm->reg_bi, bu, bi, est_d.as<double>());
+            SB2_LAUNCH_CHECK();
+            gather_f64_kernel<<<nb, 256, 0, st>>>(n, perm.as<int64_t>(), est_d.as<double>(), est_it.as<double>());
+            SB2_LAUNCH_CHECK();
+            est_u = est_d.as<double>();
+            est_i = est_it.as<double>();
+        }
+        SB2_TRY(nmf_pass(n_users, f, ptr_u.as<int64_t>(), i, r, est_u, pu_cur, qi_cur, pu_nxt, prm->reg_pu,
+                         status_d.as<int>(), st));
+        SB2_TRY(nmf_pass(n_items, f, ptr_i.as<int64_t>(), u_it.as<int32_t>(), r_it.as<double>(), est_i, qi_cur, pu_cur,
+                         qi_nxt, prm->reg_qi, status_d.as<int>(), st));
+        std::swap(pu_cur, pu_nxt);
+        std::swap(qi_cur, qi_nxt);
+    }
+    if (pu_cur != pu) {
+        SB2_CUDA(cudaMemcpyAsync(pu, pu_cur, (size_t)n_users * f * 8, cudaMemcpyDeviceToDevice, st));
+        SB2_CUDA(cudaMemcpyAsync(qi, qi_cur, (size_t)n_items * f * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    int h[2] = {0, 0};
+    SB2_CUDA(cudaMemcpyAsync(h, status_d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    if (h[1]) {
+        set_error("nmf_fit: (u, i, r) must be grouped by ascending u (all_ratings() order)");
+        return SB2_ERR_INVALID;
+    }
+    if (h[0]) {
+        set_error("float division");
+        return SB2_ERR_ZERO_DIVISION;
+    }
+    return SB2_OK;
+}
+
+}  // namespace sb2

@@ -1,0 +1,456 @@
+// Similarity matrices on the int8 tensor cores.
+//
+// Replaces similarities.pyx:28-361 of the reference.  The reference's triple loop
+//     for y: for (xi, ri) in yr[y]: for (xj, rj) in yr[y]:  freq[xi,xj] += 1; prods[xi,xj] += ri*rj; ...
+// is a set of masked dense contractions over y of the n_x x n_y rating matrix:
+//     freq = M M^T   prods = R R^T   sqi = (R.R) M^T   sqj = M (R.R)^T   si = R M^T   sj = M R^T
+// (M = [R != 0]).  Ratings are exact multiples of 1/denom, so q = r*denom is an integer; q, q^2 are
+// split into base-256 digits, each digit panel is a u8 matrix, every digit-pair product runs on
+// tcgen05.mma kind::i8 with exact int32 accumulation (sim_gemm.cu) and the digits are recombined in
+// fp64 planes (exact below 2^53).  pearson_baseline's residuals r - (mu + b_y) - b_x are expanded
+// algebraically so that the only non-integer operand is a per-y scalar a_y = mu + b_y, which is
+// quantised to 47-bit fixed point and digit-split the same way; the b_x terms are applied in the fp64
+// finalize kernel.  See DESIGN.md "Similarity path" for the algebra and the error bound.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "sim_gemm.cuh"
+
+namespace sb2 {
+
+// status words written by the kernels (device int[8])
+enum { ST_BAD_RATING = 0, ST_MAX_Q = 1, ST_DUP = 2, ST_ZERODIV = 3, ST_NWORDS = 8 };
+
+__device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ ptr, int64_t n_seg, int64_t a) {
+    int64_t lo = 0, hi = n_seg;  // largest s with ptr[s] <= a
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ptr[mid] <= a) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// pass 1: check the ratings are integer multiples of 1/denom and find max q; a_y range for baselines
+__global__ void sim_analyze_kernel(const double* __restrict__ r, int64_t nnz, double denom, int* __restrict__ status,
+                                   const double* __restrict__ y_biases, int64_t n_y, double global_mean,
+                                   double* __restrict__ a_y, unsigned long long* __restrict__ a_minmax) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < nnz) {
+        const double q = r[t] * denom;
+        const double qr = rint(q);
+        if (!(fabs(q - qr) <= 1e-9 * fmax(1.0, fabs(q))) || qr < 0.0 || qr > 65535.0)
+            atomicExch(&status[ST_BAD_RATING], 1);
+        else
+            atomicMax(&status[ST_MAX_Q], (int)qr);
+    }
+    if (y_biases != nullptr && t < n_y) {
+        const double a = global_mean + y_biases[t];  // partial_bias, similarities.pyx:337
+        a_y[t] = a;
+        // order-preserving map double -> uint64 for atomicMin/Max
+        unsigned long long b = (unsigned long long)__double_as_longlong(a);
+        b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        atomicMin(&a_minmax[0], b);
+        atomicMax(&a_minmax[1], b);
+    }
+}
+
+struct PackArgs {
+    const int64_t* y_ptr;
+    const int32_t* x_idx;
+    const double* r;
+    int64_t nnz, n_y, k_pad;
+    double denom;
+    uint8_t* m_panel;
+    uint8_t* q_panel[2];
+    int nq;
+    uint8_t* s_panel[4];
+    int ns;
+    // pearson_baseline only
+    const double* a_y;
+    double a_shift;  // integer shift c: a' = a - c >= 0
+    double a_scale;  // 2^FB
+    uint8_t* a_panel[6];
+    uint8_t* c_panel[6];
+    int na, nc;
+    int* status;
+    int64_t n_x;
+};
+
+// pass 2: scatter the yr CSR into the dense K-major u8 panels
+__global__ void sim_pack_kernel(const PackArgs p) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.nnz) return;
+    const int64_t y = find_segment(p.y_ptr, p.n_y, t);
+    const int64_t x = p.x_idx[t];
+    if (x < 0 || x >= p.n_x) {
+        atomicExch(&p.status[ST_BAD_RATING], 2);
+        return;
+    }
+    const size_t o = (size_t)x * (size_t)p.k_pad + (size_t)y;
+    // mask byte through a word atomic so that a second (x, y) hit is detected
+    unsigned* mw = reinterpret_cast<unsigned*>(p.m_panel + (o & ~(size_t)3));
+    const unsigned sh = (unsigned)(o & 3) * 8;
+    const unsigned old = atomicAdd(mw, 1u << sh);
+    if ((old >> sh) & 0xFF) {
+        atomicExch(&p.status[ST_DUP], 1);
+        return;
+    }
+    const unsigned q = (unsigned)rint(p.r[t] * p.denom);
+    for (int d = 0; d < p.nq; ++d) p.q_panel[d][o] = (uint8_t)((q >> (8 * d)) & 0xFF);
+    const unsigned long long s = (unsigned long long)q * q;
+    for (int d = 0; d < p.ns; ++d) p.s_panel[d][o] = (uint8_t)((s >> (8 * d)) & 0xFF);
+    if (p.na) {
+        const double ap = p.a_y[y] - p.a_shift;
+        const unsigned long long af = (unsigned long long)rint(ap * p.a_scale);  // < 2^48
+        for (int d = 0; d < p.na; ++d) p.a_panel[d][o] = (uint8_t)((af >> (8 * d)) & 0xFF);
+        // af^2 < 2^96: keep bits [48, 96)
+        const unsigned long long hi = __umul64hi(af, af), lo = af * af;
+        const unsigned long long cf = (hi << 16) | (lo >> 48);
+        for (int d = 0; d < p.nc; ++d) p.c_panel[d][o] = (uint8_t)((cf >> (8 * d)) & 0xFF);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// finalize: planes -> sim.  All arithmetic in round-to-nearest fp64 with the reference's operation
+// order and no FMA contraction (similarities.pyx:86-95, :155-164, :240-256, :347-359).
+// ----------------------------------------------------------------------------------------------
+struct FinArgs {
+    int kind;
+    int64_t n_x, ld;           // planes: rows x ld
+    int64_t row_begin, row_end;  // global rows covered
+    int64_t plane_row0;
+    const double* freq;
+    const double* prods;
+    const double* sqi;
+    const double* sqj;
+    const double* si;
+    const double* sj;
+    const double* t1ij;
+    const double* t1ji;
+    const double* t2;
+    const double* a1;
+    const double* bx;
+    double a_shift;
+    double inv_d, inv_d2;  // 1/denom, 1/denom^2
+    int min_support;
+    double shrinkage;
+    double* sim;  // (row_end-row_begin) x n_x
+    int* status;
+};
+
+// value of sim at (lo, hi) given the accumulators seen from (i, j); swap = (i > j)
+__device__ __forceinline__ double sim_value(const FinArgs& f, size_t o, int64_t i, int64_t j, bool swap) {
+    const double n = f.freq[o];
+    if (n < (double)f.min_support) return 0.0;
+    const double prods = __dmul_rn(f.prods[o], f.inv_d2);
+    if (f.kind == SB2_SIM_MSD) {
+        const double sqi = __dmul_rn(f.sqi[o], f.inv_d2), sqj = __dmul_rn(f.sqj[o], f.inv_d2);
+        // sum (ri-rj)^2 = sqi + sqj - 2 prods: every term is an exact multiple of 1/denom^2
+        const double sq_diff = __dsub_rn(__dadd_rn(sqi, sqj), __dmul_rn(2.0, prods));
+        if (n == 0.0) {
+            atomicExch(&f.status[ST_ZERODIV], 1);
+            return 0.0;
+        }
+        return __ddiv_rn(1.0, __dadd_rn(__ddiv_rn(sq_diff, n), 1.0));
+    }
+    double sqi = __dmul_rn((swap ? f.sqj : f.sqi)[o], f.inv_d2);
+    double sqj = __dmul_rn((swap ? f.sqi : f.sqj)[o], f.inv_d2);
+    if (f.kind == SB2_SIM_COSINE) {
+        const double denum = __dsqrt_rn(__dmul_rn(sqi, sqj));
+        return __ddiv_rn(prods, denum);
+    }
+    const double si = __dmul_rn((swap ? f.sj : f.si)[o], f.inv_d);
+    const double sj = __dmul_rn((swap ? f.si : f.sj)[o], f.inv_d);
+    if (f.kind == SB2_SIM_PEARSON) {
+        const double num = __dsub_rn(__dmul_rn(n, prods), __dmul_rn(si, sj));
+        const double vi = __dsub_rn(__dmul_rn(n, sqi), __dmul_rn(si, si));
+        const double vj = __dsub_rn(__dmul_rn(n, sqj), __dmul_rn(sj, sj));
+        const double denum = __dsqrt_rn(__dmul_rn(vi, vj));
+        return denum == 0.0 ? 0.0 : __ddiv_rn(num, denum);
+    }
+    // pearson_baseline: lo = min(i, j) plays "xi"
+    const int64_t lo = swap ? j : i, hi = swap ? i : j;
+    const double bi = f.bx[lo] + f.a_shift, bj = f.bx[hi] + f.a_shift;
+    const double t1i = (swap ? f.t1ji : f.t1ij)[o], t1j = (swap ? f.t1ij : f.t1ji)[o];
+    const double t2 = f.t2[o], a1 = f.a1[o];
+    const double pr = prods - t1i - t1j + t2 - bj * si - bi * sj + (bi + bj) * a1 + bi * bj * n;
+    double di = sqi - 2.0 * t1i + t2 - 2.0 * bi * si + 2.0 * bi * a1 + bi * bi * n;
+    double dj = sqj - 2.0 * t1j + t2 - 2.0 * bj * sj + 2.0 * bj * a1 + bj * bj * n;
+    di = fmax(di, 0.0);
+    dj = fmax(dj, 0.0);
+    double s = __ddiv_rn(pr, __dsqrt_rn(__dmul_rn(di, dj)));
+    const double fm1 = n - 1.0;
+    const double den = __dadd_rn(fm1, f.shrinkage);
+    if (den == 0.0) {
+        atomicExch(&f.status[ST_ZERODIV], 1);
+        return 0.0;
+    }
+    s = __dmul_rn(s, __ddiv_rn(fm1, den));
+    return s;
+}
+
+// symmetric build: 32x32 tiles with tj >= ti; the tile's values go to sim[i][j] and (transposed
+// through shared memory) to sim[j][i], exactly like the reference mirrors (similarities.pyx:95).
+__global__ void sim_finalize_sym_kernel(const FinArgs f) {
+    __shared__ double tile[32][33];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;
+    const int tx = threadIdx.x, ty0 = threadIdx.y;  // block 32 x 8
+    for (int ty = ty0; ty < 32; ty += 8) {
+        const int64_t i = (int64_t)ti * 32 + ty, j = (int64_t)tj * 32 + tx;
+        double s = 0.0;
+        if (i < f.n_x && j < f.n_x) {
+            if (i == j) s = 1.0;
+            else if (i < j) s = sim_value(f, (size_t)i * f.ld + j, i, j, false);
+            if (i <= j) f.sim[(size_t)i * f.n_x + j] = s;
+        }
+        tile[ty][tx] = s;
+    }
+    __syncthreads();
+    for (int ty = ty0; ty < 32; ty += 8) {
+        // element (row = tj*32+ty, col = ti*32+tx) = value at (col, row)
+        const int64_t i = (int64_t)tj * 32 + ty, j = (int64_t)ti * 32 + tx;
+        if (i < f.n_x && j < f.n_x && j < i) f.sim[(size_t)i * f.n_x + j] = tile[tx][ty];
+    }
+}
+
+// row-shard build: every (i, j) of the shard rows, accumulators valid at (i, j) itself
+__global__ void sim_finalize_rows_kernel(const FinArgs f) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t i = f.row_begin + blockIdx.y;
+    if (j >= f.n_x || i >= f.row_end) return;
+    double s;
+    if (i == j) s = 1.0;
+    else s = sim_value(f, (size_t)(i - f.plane_row0) * f.ld + j, i, j, i > j);
+    f.sim[(size_t)(i - f.row_begin) * f.n_x + j] = s;
+}
+
+// ----------------------------------------------------------------------------------------------
+// driver
+// ----------------------------------------------------------------------------------------------
+static int n_digits(unsigned long long v) {
+    int d = 1;
+    while (v >>= 8) ++d;
+    return d;
+}
+
+int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
+                  int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
+                  const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
+                  cudaStream_t st) {
+    if (kind < 0 || kind > 3 || n_x <= 0 || n_y < 0 || nnz < 0 || rating_denom <= 0 || row_begin < 0 ||
+        row_end > n_x || row_begin >= row_end) {
+        set_error("sim_build: invalid argument");
+        return SB2_ERR_INVALID;
+    }
+    const bool pb = (kind == SB2_SIM_PEARSON_BASELINE);
+    if (pb && (!x_biases || !y_biases)) {
+        set_error("sim_build: pearson_baseline needs x_biases and y_biases");
+        return SB2_ERR_INVALID;
+    }
+    if (pb && min_support < 2) min_support = 2;  // similarities.pyx:334
+    const bool full = (row_begin == 0 && row_end == n_x);
+    if (!full && row_begin % GEMM_BM) {
+        set_error("sim_build: row_begin of a shard must be a multiple of %d", GEMM_BM);
+        return SB2_ERR_INVALID;
+    }
+    const int64_t n_pad = round_up(n_x, GEMM_BM);
+    const int64_t k_pad = round_up(std::max<int64_t>(n_y, 1), GEMM_BK);
+    const int64_t rows_pad = round_up(row_end, GEMM_BM) - row_begin;  // plane rows (shard)
+    const int64_t ld = n_pad;
+
+    // ---- pass 1: analyse ratings --------------------------------------------------------------
+    DevBuf status_d, a_y_d, mm_d;
+    SB2_TRY(status_d.alloc(ST_NWORDS * sizeof(int), st));
+    SB2_CUDA(cudaMemsetAsync(status_d.p, 0, ST_NWORDS * sizeof(int), st));
+    SB2_TRY(mm_d.alloc(2 * sizeof(unsigned long long), st));
+    const unsigned long long mm_init[2] = {~0ull, 0ull};
+    SB2_CUDA(cudaMemcpyAsync(mm_d.p, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice, st));
+    if (pb) SB2_TRY(a_y_d.alloc((size_t)std::max<int64_t>(n_y, 1) * sizeof(double), st));
+    {
+        const int64_t work = std::max(nnz, pb ? n_y : (int64_t)0);
+        if (work > 0) {
+            sim_analyze_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, st>>>(
+                r, nnz, (double)rating_denom, status_d.as<int>(), pb ? y_biases : nullptr, n_y, global_mean,
+                a_y_d.as<double>(), mm_d.as<unsigned long long>());
+            SB2_LAUNCH_CHECK();
+        }
+    }
+    int status_h[ST_NWORDS];
+    unsigned long long mm_h[2];
+    SB2_CUDA(cudaMemcpyAsync(status_h, status_d.p, sizeof(status_h), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaMemcpyAsync(mm_h, mm_d.p, sizeof(mm_h), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    if (status_h[ST_BAD_RATING]) {
+        set_error("sim_build: ratings are not integer multiples of 1/%d in [0, 65535/%d]", rating_denom,
+                  rating_denom);
+        return SB2_ERR_UNSUPPORTED;
+    }
+    const unsigned long long max_q = (unsigned long long)status_h[ST_MAX_Q];
+    const int nq = n_digits(max_q), ns = n_digits(max_q * max_q);
+
+    double a_shift = 0.0, a_scale = 1.0;
+    int FB = 0, na = 0, nc = 0;
+    if (pb) {
+        auto unmap = [](unsigned long long b) {
+            b = (b >> 63) ? (b & 0x7FFFFFFFFFFFFFFFull) : ~b;
+            double d;
+            memcpy(&d, &b, sizeof(d));
+            return d;
+        };
+        double amin = n_y > 0 ? unmap(mm_h[0]) : 0.0, amax = n_y > 0 ? unmap(mm_h[1]) : 0.0;
+        if (!(amin == amin) || !(amax == amax) || fabs(amin) > 1e12 || fabs(amax) > 1e12) {
+            set_error("sim_build: non-finite baselines");
+            return SB2_ERR_INVALID;
+        }
+        a_shift = floor(amin);
+        const double range = amax - a_shift;  // a' in [0, range]
+        int ib = 1;
+        while (ldexp(1.0, ib) <= range) ++ib;
+        FB = 47 - ib;  // a' * 2^FB < 2^47 (+ rounding) fits 6 base-256 digits
+        if (FB < 16) {
+            set_error("sim_build: baseline range too wide for the fixed-point path");
+            return SB2_ERR_UNSUPPORTED;
+        }
+        a_scale = ldexp(1.0, FB);
+        na = 6;
+        nc = 6;
+    }
+
+    // ---- panels -------------------------------------------------------------------------------
+    const size_t panel_bytes = (size_t)n_pad * (size_t)k_pad;
+    const int n_panels = 1 + nq + ns + na + nc;
+    DevBuf panels_d;
+    SB2_TRY(panels_d.alloc(panel_bytes * n_panels, st));
+    SB2_CUDA(cudaMemsetAsync(panels_d.p, 0, panel_bytes * n_panels, st));
+    uint8_t* base = panels_d.as<uint8_t>();
+    int pi = 0;
+    PackArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.y_ptr = y_ptr; pa.x_idx = x_idx; pa.r = r; pa.nnz = nnz; pa.n_y = n_y; pa.k_pad = k_pad;
+    pa.denom = (double)rating_denom; pa.n_x = n_x;
+    pa.m_panel = base + panel_bytes * (pi++);
+    pa.nq = nq; pa.ns = ns; pa.na = na; pa.nc = nc;
+    for (int d = 0; d < nq; ++d) pa.q_panel[d] = base + panel_bytes * (pi++);
+    for (int d = 0; d < ns; ++d) pa.s_panel[d] = base + panel_bytes * (pi++);
+    for (int d = 0; d < na; ++d) pa.a_panel[d] = base + panel_bytes * (pi++);
+    for (int d = 0; d < nc; ++d) pa.c_panel[d] = base + panel_bytes * (pi++);
+    pa.a_y = a_y_d.as<double>(); pa.a_shift = a_shift; pa.a_scale = a_scale;
+    pa.status = status_d.as<int>();
+    if (nnz > 0) {
+        sim_pack_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, st>>>(pa);
+        SB2_LAUNCH_CHECK();
+    }
+
+    // ---- tile list ----------------------------------------------------------------------------
+    // Row blocks are walked in bands of 12; inside a band tiles go column-block-major, so the ~148
+    // tiles in flight share ~12 A-side and ~12 B-side row blocks of every panel (L2 reuse).
+    std::vector<int2> tiles;
+    {
+        const int rb0 = (int)(row_begin / GEMM_BM), rb1 = (int)ceil_div(row_end, GEMM_BM);
+        const int ncb = (int)(n_pad / GEMM_BN);
+        const int band = 12;
+        for (int b0 = rb0; b0 < rb1; b0 += band)
+            for (int cb = 0; cb < ncb; ++cb)
+                for (int rb = b0; rb < std::min(b0 + band, rb1); ++rb)
+                    if (!full || cb >= rb) tiles.push_back(make_int2(rb, cb));
+    }
+    DevBuf tiles_d;
+    SB2_TRY(tiles_d.alloc(tiles.size() * sizeof(int2), st));
+    SB2_CUDA(cudaMemcpyAsync(tiles_d.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+
+    // ---- planes + jobs ------------------------------------------------------------------------
+    enum { P_FREQ, P_PRODS, P_SQI, P_SQJ, P_SI, P_SJ, P_T1IJ, P_T1JI, P_T2, P_A1, P_COUNT };
+    bool need[P_COUNT] = {true, true, true, true, false, false, false, false, false, false};
+    if (kind == SB2_SIM_PEARSON || pb) need[P_SI] = need[P_SJ] = true;
+    if (pb) need[P_T1IJ] = need[P_T1JI] = need[P_T2] = need[P_A1] = true;
+    const size_t plane_elems = (size_t)rows_pad * (size_t)ld;
+    int n_planes = 0;
+    int plane_slot[P_COUNT];
+    for (int k = 0; k < P_COUNT; ++k) plane_slot[k] = need[k] ? n_planes++ : -1;
+    DevBuf planes_d;
+    SB2_TRY(planes_d.alloc(plane_elems * sizeof(double) * n_planes, st));
+    auto plane = [&](int k) -> double* {
+        return plane_slot[k] < 0 ? nullptr : planes_d.as<double>() + plane_elems * plane_slot[k];
+    };
+
+    std::vector<GemmJob> jobs;
+    bool started[P_COUNT] = {false};
+    auto add = [&](int pl, const uint8_t* a, const uint8_t* b, double alpha) {
+        jobs.push_back(GemmJob{a, b, plane(pl), alpha, started[pl] ? 1 : 0});
+        started[pl] = true;
+    };
+    const uint8_t* M = pa.m_panel;
+    add(P_FREQ, M, M, 1.0);
+    // most significant digit pair first (keeps partial sums exact and ordered by magnitude)
+    for (int s = 2 * (nq - 1); s >= 0; --s)
+        for (int a = nq - 1; a >= 0; --a) {
+            const int b = s - a;
+            if (b < 0 || b >= nq) continue;
+            add(P_PRODS, pa.q_panel[a], pa.q_panel[b], ldexp(1.0, 8 * s));
+        }
+    for (int d = ns - 1; d >= 0; --d) {
+        add(P_SQI, pa.s_panel[d], M, ldexp(1.0, 8 * d));
+        add(P_SQJ, M, pa.s_panel[d], ldexp(1.0, 8 * d));
+    }
+    if (need[P_SI])
+        for (int d = nq - 1; d >= 0; --d) {
+            add(P_SI, pa.q_panel[d], M, ldexp(1.0, 8 * d));
+            add(P_SJ, M, pa.q_panel[d], ldexp(1.0, 8 * d));
+        }
+    if (pb) {
+        const double inv_d = 1.0 / (double)rating_denom;
+        for (int s = na - 1; s >= 0; --s) {
+            for (int d = nq - 1; d >= 0; --d) {
+                const double alpha = ldexp(1.0, 8 * (s + d) - FB) * inv_d;
+                add(P_T1IJ, pa.q_panel[d], pa.a_panel[s], alpha);
+                add(P_T1JI, pa.a_panel[s], pa.q_panel[d], alpha);
+            }
+            add(P_A1, M, pa.a_panel[s], ldexp(1.0, 8 * s - FB));
+        }
+        for (int s = nc - 1; s >= 0; --s) add(P_T2, M, pa.c_panel[s], ldexp(1.0, 8 * s + 48 - 2 * FB));
+    }
+    if (!tiles.empty())
+        SB2_TRY(gemm_u8_tc_run(jobs.data(), (int)jobs.size(), n_pad, k_pad, tiles_d.as<int2>(), (int)tiles.size(), ld,
+                               row_begin, st));
+
+    // ---- finalize -----------------------------------------------------------------------------
+    FinArgs f;
+    memset(&f, 0, sizeof(f));
+    f.kind = kind; f.n_x = n_x; f.ld = ld; f.row_begin = row_begin; f.row_end = row_end; f.plane_row0 = row_begin;
+    f.freq = plane(P_FREQ); f.prods = plane(P_PRODS); f.sqi = plane(P_SQI); f.sqj = plane(P_SQJ);
+    f.si = plane(P_SI); f.sj = plane(P_SJ); f.t1ij = plane(P_T1IJ); f.t1ji = plane(P_T1JI);
+    f.t2 = plane(P_T2); f.a1 = plane(P_A1);
+    f.bx = x_biases; f.a_shift = a_shift;
+    f.inv_d = 1.0 / (double)rating_denom;
+    f.inv_d2 = 1.0 / ((double)rating_denom * (double)rating_denom);
+    f.min_support = min_support; f.shrinkage = shrinkage; f.sim = sim_out; f.status = status_d.as<int>();
+    if (full) {
+        const unsigned nt = (unsigned)ceil_div(n_x, 32);
+        sim_finalize_sym_kernel<<<dim3(nt, nt), dim3(32, 8), 0, st>>>(f);
+    } else {
+        sim_finalize_rows_kernel<<<dim3((unsigned)ceil_div(n_x, 256), (unsigned)(row_end - row_begin)), 256, 0, st>>>(f);
+    }
+    SB2_LAUNCH_CHECK();
+
+    SB2_CUDA(cudaMemcpyAsync(status_h, status_d.p, sizeof(status_h), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    if (status_h[ST_BAD_RATING]) {
+        set_error("sim_build: x index out of range");
+        return SB2_ERR_INVALID;
+    }
+    if (status_h[ST_DUP]) {
+        set_error("sim_build: duplicate (x, y) pair in yr -- not representable in the dense rating panels");
+        return SB2_ERR_DUPLICATE;
+    }
+    if (status_h[ST_ZERODIV]) {
+        set_error("float division");
+        return SB2_ERR_ZERO_DIVISION;
+    }
+    return SB2_OK;
+}
+
+}  // namespace sb2

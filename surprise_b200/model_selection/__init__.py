@@ -1,0 +1,4 @@
+from .split import KFold, PredefinedKFold, train_test_split
+from .validation import cross_validate, fit_and_score
+
+__all__ = ["KFold", "PredefinedKFold", "train_test_split", "cross_validate", "fit_and_score"]
