@@ -1,0 +1,55 @@
+"""Synthetic ratings of a named shape: unique (u, i) pairs drawn uniformly,
+ratings from a planted low-rank model so that held-out RMSE is informative, rounded to the scale's grid.
+Inner ids are first-appearance order of the shuffled list, as Dataset.construct_trainset assigns them
+(reference dataset.py:219-234).  Everything is seeded; nothing is read from disk."""
+import numpy as np
+
+SHAPES = {
+    "ml-100k": (943, 1682, 100_000, 1.0),
+    "ml-1m": (6040, 3706, 1_000_000, 1.0),      # BASELINE.json configs[1]
+    "ml-10m": (72_000, 10_700, 10_000_000, 0.5),
+    "ml-20m": (138_000, 27_000, 20_000_000, 0.5),
+    "netflix": (480_000, 17_700, 100_000_000, 1.0),
+}
+
+
+def ratings(n_users, n_items, n_ratings, step=1.0, seed=0, holdout=0.1, rank=8):
+    """Returns dict(train=(u, i, r), test=(u, i, r), n_users, n_items) with compact inner ids for the train
+    part (users / items that only occur in the test part get id -1 there = unknown)."""
+    rng = np.random.default_rng(seed)
+    n_total = int(round(n_ratings * (1 + holdout)))
+    if n_total > 0.5 * n_users * n_items:
+        raise ValueError("shape too dense for the unique-pair sampler")
+    lin = np.unique(rng.integers(0, n_users * n_items, int(n_total * 1.08) + 16, dtype=np.int64))
+    while len(lin) < n_total:
+        extra = rng.integers(0, n_users * n_items, n_total, dtype=np.int64)
+        lin = np.unique(np.concatenate((lin, extra)))
+    lin = rng.permutation(lin)[:n_total]
+    u_raw = (lin // n_items).astype(np.int64)
+    i_raw = (lin % n_items).astype(np.int64)
+    bu = rng.normal(0, .4, n_users)
+    bi = rng.normal(0, .4, n_items)
+    p = rng.normal(0, .35, (n_users, rank))
+    q = rng.normal(0, .35, (n_items, rank))
+    r = 3.5 + bu[u_raw] + bi[i_raw] + np.einsum("kf,kf->k", p[u_raw], q[i_raw]) + rng.normal(0, .8, n_total)
+    lo = step if step < 1 else 1.0
+    r = np.clip(np.round(r / step) * step, lo, 5.0)
+
+    def first_appearance(a, n):
+        uniq, first = np.unique(a, return_index=True)
+        order = np.argsort(first, kind="stable")
+        rank_of = np.full(n, -1, dtype=np.int64)
+        rank_of[uniq[order]] = np.arange(len(uniq))
+        return rank_of
+
+    n_tr = n_ratings
+    map_u = first_appearance(u_raw[:n_tr], n_users)
+    map_i = first_appearance(i_raw[:n_tr], n_items)
+    tr = (map_u[u_raw[:n_tr]].astype(np.int32), map_i[i_raw[:n_tr]].astype(np.int32), r[:n_tr].copy())
+    te = (map_u[u_raw[n_tr:]].astype(np.int32), map_i[i_raw[n_tr:]].astype(np.int32), r[n_tr:].copy())
+    return dict(train=tr, test=te, n_users=int(map_u.max()) + 1, n_items=int(map_i.max()) + 1)
+
+
+def shaped(name, seed=0, scale=1.0):
+    nu, ni, n, step = SHAPES[name]
+    return ratings(int(nu * scale), int(ni * scale), int(n * scale * scale), step=step, seed=seed)

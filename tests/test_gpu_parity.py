@@ -1,0 +1,425 @@
+"""Parity tests proper: the CUDA path (through the C-ABI / the reference-shaped Python API) against the
+C oracle and the golden vectors.  Bit-exact for similarities on integer / half-integer ratings, NMF
+factors, ALS / SGD baselines and k-NN estimates; 1e-9 absolute for pearson_baseline and float ratings;
+held-out RMSE / MAE within 0.005 for SVD (stratified update order)."""
+import ctypes as C
+import hashlib
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, inner_pairs, rmse_mae
+
+pytestmark = pytest.mark.gpu
+
+import surprise_b200 as sb  # noqa: E402
+from surprise_b200 import _native as nat  # noqa: E402
+from surprise_b200 import similarities as sims  # noqa: E402
+from surprise_b200 import synth  # noqa: E402
+
+KINDS = ("cosine", "msd", "pearson", "pearson_baseline")
+PB_ATOL = 1e-9  # north_star: stated tolerance for the floating-point similarity path
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_device_is_blackwell():
+    sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    nat.check(nat.lib().sb2_device_info(C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
+    assert maj.value == 10, "kernels are built for sm_100a only"
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 1024), (512, 128, 4096 + 64)])
+def test_tcgen05_gemm_against_dp4a_and_numpy(shape):
+    import torch
+    m, n, k = shape
+    rng = np.random.RandomState(m + n + k)
+    a = rng.randint(0, 256, (m, k)).astype(np.uint8)
+    b = rng.randint(0, 256, (n, k)).astype(np.uint8)
+    da, db = nat.to_dev(a, np.uint8), nat.to_dev(b, np.uint8)
+    c_tc = nat.empty_dev((m, n), np.int32)
+    c_ref = nat.empty_dev((m, n), np.int32)
+    nat.check(nat.lib().sb2_gemm_u8_selftest_dev(1, m, n, k, nat.ptr(da), nat.ptr(db), nat.ptr(c_tc), nat.stream()))
+    nat.check(nat.lib().sb2_gemm_u8_selftest_dev(0, m, n, k, nat.ptr(da), nat.ptr(db), nat.ptr(c_ref), nat.stream()))
+    torch.cuda.synchronize()
+    want = a.astype(np.int64) @ b.astype(np.int64).T
+    assert np.array_equal(c_ref.cpu().numpy(), want)
+    assert np.array_equal(c_tc.cpu().numpy(), want)
+
+
+# ---- similarities -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("ms", (1, 4))
+def test_toy_similarities(toy, kind, ms):
+    yr = (toy["y_ptr"], toy["x_idx"], toy["r"])
+    if kind == "pearson_baseline":
+        got = sims.pearson_baseline(8, yr, ms, float(toy["global_mean"]), toy["bx"], toy["by"])
+        assert np.allclose(got, toy["%s_%d" % (kind, ms)], rtol=0, atol=PB_ATOL)
+        assert np.array_equal(got == 0, toy["%s_%d" % (kind, ms)] == 0)  # freq / min_support mask is exact
+    else:
+        got = getattr(sims, kind)(8, yr, ms)
+        assert np.array_equal(got, toy["%s_%d" % (kind, ms)])
+    assert np.array_equal(got, got.T) and np.all(np.diag(got) == 1)
+
+
+def test_toy_dict_input_and_shuffle(toy):
+    """The reference API takes a dict of lists; order inside a list must not matter."""
+    import random
+    yr = {0: [(0, 3), (1, 3), (2, 3), (5, 1), (6, 1.5), (7, 3)], 1: [(0, 4), (1, 4), (2, 4)],
+          2: [(2, 5), (3, 2), (4, 3)], 3: [(1, 1), (2, 4), (3, 2), (4, 3), (5, 3), (6, 3.5), (7, 2)],
+          4: [(1, 5), (2, 1), (5, 2), (6, 2.5), (7, 2.5)]}
+    random.seed(0)
+    for v in yr.values():
+        random.shuffle(v)
+    assert np.array_equal(sims.cosine(8, yr, 1), toy["cosine_1"])
+    assert np.array_equal(sims.msd(8, yr, 1), toy["msd_1"])
+    assert np.array_equal(sims.pearson(8, yr, 4), toy["pearson_4"])
+    s0 = sims.pearson_baseline(8, yr, 1, 3, toy["bx"], toy["by"], 0)
+    assert np.allclose(s0, toy["pearson_baseline_shr0"], rtol=0, atol=PB_ATOL)
+    s7 = sims.pearson_baseline(8, yr, 2, 3, toy["bx"], toy["by"], shrinkage=7.5)
+    assert np.allclose(s7, toy["pearson_baseline_shr7p5"], rtol=0, atol=PB_ATOL)
+
+
+@pytest.mark.parametrize("orient", ("item", "user"))
+def test_u1_similarities_bit_exact(u1, u1_golden, u1_arrays, orient):
+    ts, _ = u1
+    ub = orient == "user"
+    n_x = ts.n_users if ub else ts.n_items
+    yr = ts.item_csr() if ub else ts.user_csr()
+    for kind in ("cosine", "msd", "pearson"):
+        got = getattr(sims, kind)(n_x, yr, 1)
+        g = u1_golden["sims"]["%s_%s_ms1" % (kind, orient)]
+        assert sha(got) == g["sha256"], kind
+        assert int(np.count_nonzero(got)) == g["nnz"]
+    assert sha(sims.cosine(n_x, yr, 3)) == u1_golden["sims"]["cosine_%s_ms3" % orient]["sha256"]
+    bu, bi = u1_arrays["als_bu"], u1_arrays["als_bi"]
+    bx, by = (bu, bi) if ub else (bi, bu)
+    got = sims.pearson_baseline(n_x, yr, 1, float(ts.global_mean), bx, by)
+    want = oracle.similarity("pearson_baseline", n_x, *yr, 1, float(ts.global_mean), bx, by, 100.0)
+    assert sha(want) == u1_golden["sims"]["pearson_baseline_%s_ms1" % orient]["sha256"]
+    assert np.allclose(got, want, rtol=0, atol=PB_ATOL)
+    assert np.array_equal(got == 0, want == 0)
+    assert np.array_equal(got, got.T)
+
+
+def test_u1_row_shard_equals_full(u1):
+    ts, _ = u1
+    yr = ts.user_csr()
+    full = sims.cosine(ts.n_items, yr, 1)
+    for kind in ("cosine", "pearson"):
+        full = getattr(sims, kind)(ts.n_items, yr, 1)
+        for (b, e) in ((0, 128), (128, 512), (1152, ts.n_items)):
+            blk = sims.build_device(kind, ts.n_items, yr, 1, row_begin=b, row_end=e).cpu().numpy()
+            assert np.array_equal(blk, full[b:e]), (kind, b, e)
+
+
+def test_float_ratings_similarities(floats):
+    """Jester-style two-decimal ratings run on the digit-split exact-integer path (denominator 100)."""
+    ds = sb.Dataset.load_from_arrays(floats["uid"], floats["iid"], floats["rating"], sb.Reader(rating_scale=(-10, 10)))
+    ts = ds.build_full_trainset()
+    assert sims.rating_denominator(ts.user_csr()[2]) == 100
+    for ub, o in ((False, "item"), (True, "user")):
+        n_x = ts.n_users if ub else ts.n_items
+        yr = ts.item_csr() if ub else ts.user_csr()
+        bx, by = (floats["als_bu"], floats["als_bi"]) if ub else (floats["als_bi"], floats["als_bu"])
+        for kind in KINDS:
+            if kind == "pearson_baseline":
+                got = sims.pearson_baseline(n_x, yr, 2, float(ts.global_mean), bx, by)
+            else:
+                got = getattr(sims, kind)(n_x, yr, 2)
+            want = floats["sim_%s_%s" % (kind, o)]
+            assert np.allclose(got, want, rtol=0, atol=PB_ATOL, equal_nan=True), (kind, o, np.abs(got - want).max())
+
+
+def test_similarity_errors():
+    with pytest.raises(ZeroDivisionError):
+        sims.msd(2, {0: [(0, 3.0)], 1: [(1, 4.0)]}, 0)
+    with pytest.raises(ValueError):
+        sims.cosine(2, {0: [(0, 3.0), (0, 4.0), (1, 2.0)]}, 1)   # duplicate (x, y)
+    with pytest.raises(ValueError):
+        sims.cosine(2, {0: [(0, np.pi), (1, 2.0)]}, 1)            # not on a 1/d grid
+    empty = sims.cosine(3, {}, 1)
+    assert np.array_equal(empty, np.eye(3))
+
+
+def test_synthetic_half_star_similarity_sampled():
+    """ml-20M-style half-star ratings at a reduced shape: sampled entries against the oracle (bit-exact
+    for the integer kinds), plus symmetry / diagonal / bounds on the whole matrix."""
+    d = synth.ratings(3000, 1500, 200_000, step=0.5, seed=3)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"], (0.5, 5.0), 0)
+    yr = ts.user_csr()
+    n_x = ts.n_items
+    o = np.lexsort((u, i))
+    xptr = np.concatenate(([0], np.cumsum(np.bincount(i, minlength=n_x)))).astype(np.int64)
+    rng = np.random.RandomState(0)
+    pi, pj = rng.randint(0, n_x, 20000), rng.randint(0, n_x, 20000)
+    mu = float(ts.global_mean)
+    bu, bi = oracle.baseline_als(ts.n_users, ts.n_items, *ts.user_csr(), *ts.item_csr(), mu)
+    for kind in KINDS:
+        if kind == "pearson_baseline":
+            got = sims.pearson_baseline(n_x, yr, 1, mu, bi, bu)
+        else:
+            got = getattr(sims, kind)(n_x, yr, 2)
+        want = oracle.similarity_pairs(kind, pi, pj, xptr, u[o], r[o], 1 if kind == "pearson_baseline" else 2, mu,
+                                       bi, bu, 100.0)
+        if kind == "pearson_baseline":
+            assert np.allclose(got[pi, pj], want, rtol=0, atol=PB_ATOL), np.abs(got[pi, pj] - want).max()
+        else:
+            assert np.array_equal(got[pi, pj], want), kind
+        assert np.array_equal(got, got.T) and np.all(np.diag(got) == 1)
+        assert np.nanmax(np.abs(got)) <= 1 + 1e-12
+
+
+# ---- baselines ----------------------------------------------------------------------------------------
+def test_u1_baselines_bit_exact(u1, u1_golden):
+    ts, _ = u1
+    algo = sb.BaselineOnly()
+    algo.fit(ts)
+    assert sha(algo.bu) == u1_golden["baseline_als"]["bu_sha256"]
+    assert sha(algo.bi) == u1_golden["baseline_als"]["bi_sha256"]
+    algo = sb.BaselineOnly(bsl_options={"method": "sgd"})
+    algo.fit(ts)
+    assert sha(algo.bu) == u1_golden["baseline_sgd"]["bu_sha256"]
+    assert sha(algo.bi) == u1_golden["baseline_sgd"]["bi_sha256"]
+    with pytest.raises(ValueError):
+        sb.BaselineOnly(bsl_options={"method": "nope"}).fit(ts)
+
+
+# ---- k-NN -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("orient", ("item", "user"))
+@pytest.mark.parametrize("kind", KINDS)
+def test_u1_knnbasic_end_to_end(u1, u1_golden, u1_arrays, kind, orient):
+    ts, testset = u1
+    algo = sb.KNNBasic(sim_options={"name": kind, "user_based": orient == "user", "min_support": 1})
+    preds = algo.fit(ts).test(testset)
+    tag = "KNNBasic_%s_%s_ms1" % (kind, orient)
+    g = u1_golden["algos"][tag]
+    est = np.array([p.est for p in preds])
+    ak = np.array([p.details.get("actual_k", -1) for p in preds])
+    assert sum(p.details["was_impossible"] for p in preds) == g["n_impossible"]
+    if kind == "pearson_baseline":
+        assert np.allclose(est, u1_arrays[tag + "_est"], rtol=0, atol=1e-6)
+        assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(g["rmse"])) < 1e-7
+    else:
+        assert np.array_equal(est, u1_arrays[tag + "_est"])
+        assert np.array_equal(ak, u1_arrays[tag + "_actual_k"])
+        assert repr(float(sb.accuracy.rmse(preds, verbose=False))) == g["rmse"]   # config 1: to the last bit
+        assert repr(float(sb.accuracy.mae(preds, verbose=False))) == g["mae"]
+    for p in preds:
+        if not p.details["was_impossible"]:
+            assert algo.min_k <= p.details["actual_k"] <= algo.k
+
+
+@pytest.mark.parametrize("orient", ("item", "user"))
+def test_u1_knn_kernel_against_oracle_on_same_sim(u1, u1_arrays, orient):
+    """Select + ordered-sum kernel in isolation: same sim matrix in, bit-identical estimates out."""
+    ts, testset = u1
+    ub = orient == "user"
+    iu, ii = inner_pairs(ts, testset)
+    x, y = (iu, ii) if ub else (ii, iu)
+    n_x = ts.n_users if ub else ts.n_items
+    ptr, idx, val = ts.item_csr() if ub else ts.user_csr()
+    mu = float(ts.global_mean)
+    bu, bi = u1_arrays["als_bu"], u1_arrays["als_bi"]
+    bx, by = (bu, bi) if ub else (bi, bu)
+    sim = oracle.similarity("pearson_baseline", n_x, ptr, idx, val, 1, mu, bx, by, 100.0)
+    for (k, min_k, mode) in ((40, 1, 0), (5, 2, 0), (40, 1, 1 if ub else 2), (10, 3, 1 if ub else 2), (1, 1, 0)):
+        want = oracle.knn_estimate(x, y, sim, ptr, idx, val, k, min_k, mode, mu, bx, by)
+        est = np.empty(len(x)); ak = np.empty(len(x), dtype=np.int32); imp = np.empty(len(x), dtype=np.uint8)
+        n_y = len(ptr) - 1
+        rc = nat.lib().sb2_knn_predict(len(x), nat.hptr(np.ascontiguousarray(x)), nat.hptr(np.ascontiguousarray(y)),
+                                       n_x, n_y, nat.hptr(sim), nat.hptr(ptr), nat.hptr(idx), nat.hptr(val), k, min_k,
+                                       mode, mu, nat.hptr(np.ascontiguousarray(bx)), nat.hptr(np.ascontiguousarray(by)),
+                                       nat.hptr(est), nat.hptr(ak), nat.hptr(imp))
+        nat.check(rc)
+        assert np.array_equal(imp, want[2]), (k, min_k, mode)
+        assert np.array_equal(ak, want[1]), (k, min_k, mode)
+        assert np.array_equal(est, want[0]), (k, min_k, mode)
+
+
+@pytest.mark.parametrize("orient", ("item", "user"))
+def test_u1_knnbaseline_end_to_end(u1, u1_golden, u1_arrays, orient):
+    ts, testset = u1
+    ub = orient == "user"
+    algo = sb.KNNBaseline(k=10, min_k=3, sim_options={"name": "msd", "user_based": ub})
+    preds = algo.fit(ts).test(testset)
+    tag = "KNNBaseline_msd_k10_mk3_" + orient
+    assert np.array_equal(np.array([p.est for p in preds]), u1_arrays[tag + "_est"])
+    assert np.array_equal(np.array([p.details.get("actual_k", -1) for p in preds]), u1_arrays[tag + "_actual_k"])
+    assert repr(float(sb.accuracy.rmse(preds, verbose=False))) == u1_golden["algos"][tag]["rmse"]
+    algo = sb.KNNBaseline(sim_options={"name": "pearson_baseline", "user_based": ub})
+    preds = algo.fit(ts).test(testset)
+    tag = "KNNBaseline_pb_" + orient
+    assert np.allclose(np.array([p.est for p in preds]), u1_arrays[tag + "_est"], rtol=0, atol=1e-6)
+    assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(u1_golden["algos"][tag]["rmse"])) < 1e-7
+
+
+def test_knn_long_lists_and_ties():
+    """Lists longer than the per-warp cache and many tied similarities (stable selection order)."""
+    rng = np.random.RandomState(1)
+    n_x, n_y = 1500, 3
+    ptr = np.array([0, 1400, 1400 + 900, 1400 + 900 + 5], dtype=np.int64)
+    idx = np.concatenate([rng.permutation(n_x)[:1400], rng.permutation(n_x)[:900], rng.permutation(n_x)[:5]]).astype(np.int32)
+    val = rng.randint(1, 6, len(idx)).astype(np.float64)
+    sim = np.round(rng.rand(n_x, n_x) * 8) / 8 - 0.25   # heavy ties, some <= 0
+    sim = (sim + sim.T) / 2
+    np.fill_diagonal(sim, 1)
+    x = rng.randint(0, n_x, 300).astype(np.int32); y = rng.randint(0, n_y, 300).astype(np.int32)
+    x[:5] = -1
+    bx = rng.normal(0, 1, n_x); by = rng.normal(0, 1, n_y)
+    for (k, min_k, mode) in ((40, 1, 0), (1000, 1, 0), (40, 1, 1), (3, 5, 2)):
+        want = oracle.knn_estimate(x, y, sim, ptr, idx, val, k, min_k, mode, 3.1, bx, by)
+        est = np.empty(len(x)); ak = np.empty(len(x), dtype=np.int32); imp = np.empty(len(x), dtype=np.uint8)
+        nat.check(nat.lib().sb2_knn_predict(len(x), nat.hptr(x), nat.hptr(y), n_x, n_y, nat.hptr(sim), nat.hptr(ptr),
+                                            nat.hptr(idx), nat.hptr(val), k, min_k, mode, 3.1, nat.hptr(bx),
+                                            nat.hptr(by), nat.hptr(est), nat.hptr(ak), nat.hptr(imp)))
+        assert np.array_equal(imp, want[2]) and np.array_equal(ak, want[1]) and np.array_equal(est, want[0])
+
+
+# ---- NMF ------------------------------------------------------------------------------------------------
+def test_u1_nmf_bit_exact(u1, u1_golden, u1_arrays):
+    ts, testset = u1
+    algo = sb.NMF(random_state=0).fit(ts)
+    g = u1_golden["algos"]["NMF_rs0"]
+    assert sha(algo.pu) == g["pu_sha256"] and sha(algo.qi) == g["qi_sha256"]
+    preds = algo.test(testset)
+    assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(g["rmse"])) < 1e-12
+    assert sum(p.details["was_impossible"] for p in preds) == g["n_impossible"]
+    algo = sb.NMF(random_state=3, n_factors=7, n_epochs=3, reg_pu=.1, reg_qi=.02).fit(ts)
+    g = u1_golden["algos"]["NMF_rs3_f7_e3"]
+    assert sha(algo.pu) == g["pu_sha256"] and sha(algo.qi) == g["qi_sha256"]
+    algo = sb.NMF(random_state=0, biased=True).fit(ts)
+    assert np.array_equal(algo.bu, u1_arrays["NMF_rs0_biased_bu"])
+    preds = algo.test(testset)
+    assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(u1_golden["algos"]["NMF_rs0_biased"]["rmse"])) < 1e-12
+    with pytest.raises(ValueError):
+        sb.NMF(init_low=-1)
+
+
+@pytest.mark.parametrize("f", (3, 15, 16, 40))
+def test_synthetic_nmf_bit_exact_host_abi(f):
+    """Through the host-buffer C-ABI, ragged segments, several group widths."""
+    d = synth.ratings(700, 300, 30_000, seed=f)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    uu, ii, rr = ts.coo()
+    rng = np.random.RandomState(f)
+    pu0 = rng.uniform(0, 1, (ts.n_users, f)); qi0 = rng.uniform(0, 1, (ts.n_items, f))
+    for biased in (False, True):
+        want = oracle.nmf_sgd(ts.n_users, ts.n_items, uu, ii, rr, np.diff(ts.user_csr()[0]), np.diff(ts.item_csr()[0]),
+                              pu0, qi0, 4, biased, float(ts.global_mean), .06, .05, .02, .03, .005, .004)
+        pu, qi = pu0.copy(), qi0.copy()
+        bu, bi = np.empty(ts.n_users), np.empty(ts.n_items)
+        prm = nat.NmfParams(n_factors=f, n_epochs=4, biased=int(biased), reserved=0, global_mean=float(ts.global_mean),
+                            reg_pu=.06, reg_qi=.05, reg_bu=.02, reg_bi=.03, lr_bu=.005, lr_bi=.004)
+        nat.check(nat.lib().sb2_nmf_fit(ts.n_users, ts.n_items, len(rr), nat.hptr(uu), nat.hptr(ii), nat.hptr(rr),
+                                        C.byref(prm), nat.hptr(pu), nat.hptr(qi), nat.hptr(bu), nat.hptr(bi)))
+        for got, w, name in ((pu, want[0], "pu"), (qi, want[1], "qi"), (bu, want[2], "bu"), (bi, want[3], "bi")):
+            assert np.array_equal(got, w), (f, biased, name)
+
+
+# ---- SVD ------------------------------------------------------------------------------------------------
+RMSE_TOL = 0.005  # north_star: SVD / SVD++ held-out RMSE / MAE within 0.005 of the reference
+
+
+@pytest.mark.parametrize("tag,kw", [("SVD_rs0", {}), ("SVD_rs0_unbiased", {"biased": False}),
+                                    ("SVD_rs0_f20_e5", {"n_factors": 20, "n_epochs": 5})])
+def test_u1_svd_rmse(u1, u1_golden, tag, kw):
+    ts, testset = u1
+    algo = sb.SVD(random_state=0, **kw).fit(ts)
+    assert algo.pu.shape == (ts.n_users, algo.n_factors) and algo.pu.dtype == np.float64
+    preds = algo.test(testset)
+    g = u1_golden["algos"][tag]
+    assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(g["rmse"])) <= RMSE_TOL
+    assert abs(float(sb.accuracy.mae(preds, verbose=False)) - float(g["mae"])) <= RMSE_TOL
+    assert sum(p.details["was_impossible"] for p in preds) == g["n_impossible"]
+
+
+def test_svd_zero_epochs_returns_init(u1):
+    ts, _ = u1
+    algo = sb.SVD(random_state=5, n_epochs=0, n_factors=10).fit(ts)
+    rng = np.random.RandomState(5)
+    pu0 = rng.normal(0, .1, (ts.n_users, 10))
+    assert np.allclose(algo.pu, pu0.astype(np.float32), rtol=0, atol=0) and np.all(algo.bu == 0)
+
+
+@pytest.mark.parametrize("f", (8, 20, 100))
+def test_synthetic_svd_rmse_vs_oracle(f):
+    """ml-1M-style synthetic at reduced size: same seed, same hyper-parameters, held-out RMSE vs the oracle's
+    sequential SGD.  Also: one epoch on a conflict-free input must equal the oracle to fp32 accuracy."""
+    d = synth.ratings(2000, 1200, 150_000, seed=10 + f)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    uu, ii, rr = ts.coo()
+    tu, ti, tr_ = d["test"]
+    mu = float(ts.global_mean)
+    algo = sb.SVD(n_factors=f, n_epochs=10, random_state=1).fit(ts)
+    rng = np.random.RandomState(1)
+    pu0 = rng.normal(0, .1, (ts.n_users, f)); qi0 = rng.normal(0, .1, (ts.n_items, f))
+    pu, qi, bu, bi = oracle.svd_sgd(uu, ii, rr, pu0, qi0, 10, True, mu, *([.005] * 4), *([.02] * 4))
+    want, _ = oracle.mf_estimate(tu, ti, True, mu, pu, qi, bu, bi)
+    got, _ = oracle.mf_estimate(tu, ti, True, mu, algo.pu, algo.qi, algo.bu, algo.bi)
+    rm_w = np.sqrt(np.mean((np.clip(want, 1, 5) - tr_) ** 2)); rm_g = np.sqrt(np.mean((np.clip(got, 1, 5) - tr_) ** 2))
+    ma_w = np.mean(np.abs(np.clip(want, 1, 5) - tr_)); ma_g = np.mean(np.abs(np.clip(got, 1, 5) - tr_))
+    assert abs(rm_w - rm_g) <= RMSE_TOL and abs(ma_w - ma_g) <= RMSE_TOL, (rm_w, rm_g)
+
+
+def test_svd_conflict_free_input_matches_oracle():
+    """A permutation matrix of ratings (no two share a user or an item) makes SGD order-independent:
+    the stratified kernel must then reproduce the sequential oracle up to fp32 rounding."""
+    n = 500
+    rng = np.random.RandomState(2)
+    u = np.arange(n, dtype=np.int32); i = rng.permutation(n).astype(np.int32)
+    r = rng.randint(1, 6, n).astype(np.float64)
+    ts = sb.Trainset.from_coo(u, i, r, n, n)
+    for biased in (True, False):
+        algo = sb.SVD(n_factors=12, n_epochs=3, random_state=4, biased=biased).fit(ts)
+        rs = np.random.RandomState(4)
+        pu0 = rs.normal(0, .1, (n, 12)); qi0 = rs.normal(0, .1, (n, 12))
+        pu, qi, bu, bi = oracle.svd_sgd(u, i, r, pu0, qi0, 3, biased, float(ts.global_mean), *([.005] * 4), *([.02] * 4))
+        assert np.allclose(algo.pu, pu, rtol=0, atol=2e-6) and np.allclose(algo.qi, qi, rtol=0, atol=2e-6)
+        assert np.allclose(algo.bu, bu, rtol=0, atol=2e-6) and np.allclose(algo.bi, bi, rtol=0, atol=2e-6)
+
+
+def test_mf_predict_against_oracle(u1):
+    ts, testset = u1
+    iu, ii = inner_pairs(ts, testset)
+    rng = np.random.RandomState(0)
+    for f in (1, 15, 100, 130):
+        pu = rng.normal(0, 1, (ts.n_users, f)); qi = rng.normal(0, 1, (ts.n_items, f))
+        bu = rng.normal(0, 1, ts.n_users); bi = rng.normal(0, 1, ts.n_items)
+        for biased in (True, False):
+            want, wimp = oracle.mf_estimate(iu, ii, biased, 3.5, pu, qi, bu, bi)
+            est = np.empty(len(iu)); imp = np.empty(len(iu), dtype=np.uint8)
+            nat.check(nat.lib().sb2_mf_predict(len(iu), nat.hptr(iu), nat.hptr(ii), ts.n_users, ts.n_items, f,
+                                               int(biased), 3.5, nat.hptr(pu), nat.hptr(qi), nat.hptr(bu), nat.hptr(bi),
+                                               None, None, None, nat.hptr(est), nat.hptr(imp)))
+            assert np.array_equal(imp, wimp)
+            assert np.allclose(est, want, rtol=1e-12, atol=1e-12)
+
+
+# ---- API behaviour ----------------------------------------------------------------------------------------
+def test_unknown_user_or_item_and_pickle(tmp_path):
+    """reference tests/test_algorithms.py::test_unknown_user_or_item + tests/test_dump.py."""
+    reader = sb.Reader(line_format="user item rating", sep=" ", skip_lines=3, rating_scale=(1, 5))
+    data = sb.Dataset.load_from_file(os.path.join(GOLDEN, "custom_dataset"), reader)
+    ts = data.build_full_trainset()
+    for klass in (sb.SVD, sb.NMF, sb.KNNBasic, sb.KNNBaseline, sb.BaselineOnly):
+        algo = klass()
+        algo.fit(ts)
+        algo.predict("user0", "unknown_item", None)
+        algo.predict("unkown_user", "item0", None)
+        p = algo.predict("unkown_user", "unknown_item", None)
+        assert 1 <= p.est <= 5
+        q = algo.predict("user0", "item0", 4)
+        sb.dump.dump(str(tmp_path / "a.pkl"), algo=algo)
+        _, algo2 = sb.dump.load(str(tmp_path / "a.pkl"))
+        assert algo2.predict("user0", "item0", 4).est == q.est
+    with pytest.raises(NameError):
+        sb.KNNBasic(sim_options={"name": "wrong"}).fit(ts)

@@ -186,7 +186,8 @@ def test_u1_knn_estimates_bit_exact(u1, u1_golden, u1_arrays, orient):
     sim = oracle.similarity("cosine", n_x, ptr, idx, val, 1)
     est, ak, imp = oracle.knn_estimate(x, y, sim, ptr, idx, val, 40, 1)
     tag = "KNNBasic_cosine_%s_ms1" % orient
-    est = np.where(imp > 0, mu, est)
+    lo, hi = ts.rating_scale
+    est = np.clip(np.where(imp > 0, mu, est), lo, hi)  # Prediction.est is clipped (algo_base.py:166-169)
     assert np.array_equal(est, u1_arrays[tag + "_est"])
     assert np.array_equal(np.where(imp > 0, -1, ak), u1_arrays[tag + "_actual_k"])
     assert int(imp.sum()) == u1_golden["algos"][tag]["n_impossible"]
@@ -195,7 +196,6 @@ def test_u1_knn_estimates_bit_exact(u1, u1_golden, u1_arrays, orient):
     sim = oracle.similarity("pearson_baseline", n_x, ptr, idx, val, 1, mu, bx, by, 100.0)
     est, ak, imp = oracle.knn_estimate(x, y, sim, ptr, idx, val, 40, 1, 1 if ub else 2, mu, bx, by)
     tag = "KNNBaseline_pb_" + orient
-    lo, hi = ts.rating_scale
     assert np.array_equal(np.clip(est, lo, hi), u1_arrays[tag + "_est"])
     assert np.array_equal(ak, u1_arrays[tag + "_actual_k"])
     sim = oracle.similarity("msd", n_x, ptr, idx, val, 1)
