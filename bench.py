@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: SVD rating-updates/s (configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload: SVD(n_factors=100, n_epochs=20, random_state=0) on ml-1M-shaped synthetic ratings
+(6040 x 3706, 1M ratings; surprise_b200/synth.py, seed 0).  One "step" = one complete fit = 20 epochs =
+2e7 rating updates.  Prints ONE JSON line (rank 0):
+
+  value        rating-updates/s with the inputs (all_ratings COO + initial factors) resident in HBM; the step
+               still contains everything sgd() does: stratification of the ratings, the 20-epoch DSGD kernel,
+               conversion of the factors back to float64.
+  e2e          the same metric through the host-buffer C-ABI call sb2_svd_fit (pinned host arrays in, host
+               arrays out; H2D / D2H inside the timed region).
+  roofline     the DSGD kernel alone (CUDA events around its launches inside the timed region) against the
+               measured HBM peak, with the algorithmic bytes per update of DESIGN.md (2*(2f+2)*4+12 = 1628 B).
+  cpu_baseline the reference's own Cython SVD.sgd (oracle/_ref, unmodified) on one host core, bounded sample.
+
+--impl reference times the reference's SVD.sgd through its own API on the host (rank 0 only).
+For N > 1 the fit is sharded over the ranks (surprise_b200/distributed.py: item blocks rotate rank -> rank over
+NCCL P2P); total work is fixed, so "scaling" is "strong".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FACTORS, N_EPOCHS, SEED = 100, 20, 0
+SHAPE = "ml-1m"
+WORKLOAD = ("SVD n_factors=100 n_epochs=20 random_state=0 on ml-1M-shaped synthetic ratings "
+            "(6040x3706, 1M ratings, integer stars, seed 0)")
+METRIC, UNIT = "SVD rating-updates/s", "rating-updates/s"
+
+
+def load_workload():
+    from surprise_b200 import synth
+    from surprise_b200.trainset import Trainset
+    d = synth.shaped(SHAPE, seed=SEED)
+    u, i, r = d["train"]
+    ts = Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    uu, ii, rr = ts.coo()  # all_ratings() order
+    rng = np.random.RandomState(SEED)
+    pu0 = rng.normal(0, .1, (ts.n_users, N_FACTORS))
+    qi0 = rng.normal(0, .1, (ts.n_items, N_FACTORS))
+    return ts, np.ascontiguousarray(uu), np.ascontiguousarray(ii), np.ascontiguousarray(rr), pu0, qi0, d["test"]
+
+
+def sgd_params(nat, mu, n_epochs=N_EPOCHS):
+    return nat.SgdParams(n_factors=N_FACTORS, n_epochs=n_epochs, biased=1, reserved=0, global_mean=mu, lr_bu=.005,
+                         lr_bi=.005, lr_pu=.005, lr_qi=.005, lr_yj=0., reg_bu=.02, reg_bi=.02, reg_pu=.02, reg_qi=.02,
+                         reg_yj=0.)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# --------------------------------------------------------------------------------------------------------------
+def reference_trainset(ref, ts, n_keep=None):
+    """The reference's own Trainset (dict-of-lists of tuples) for the first n_keep ratings in all_ratings order."""
+    ptr, idx, val = ts.user_csr()
+    n_keep = ts.n_ratings if n_keep is None else n_keep
+    ur, ir = {}, {}
+    idx_l, val_l = idx.tolist(), val.tolist()
+    kept = 0
+    for u in range(ts.n_users):
+        b, e = int(ptr[u]), int(ptr[u + 1])
+        if kept + (e - b) > n_keep:
+            e = b + (n_keep - kept)
+        if e <= b:
+            break
+        ur[u] = list(zip(idx_l[b:e], val_l[b:e]))
+        kept += e - b
+    for u, lst in ur.items():
+        for (i, r) in lst:
+            ir.setdefault(i, []).append((u, r))
+    n_items = max(ir) + 1
+    for i in range(n_items):
+        ir.setdefault(i, [])
+    return ref.Trainset(ur, ir, len(ur), n_items, kept, (1, 5), 0, {}, {}), kept
+
+
+def cpu_sgd_rate(ts, uu, ii, rr, pu0, qi0, n_ratings, n_epochs):
+    """Time the reference's Cython SVD.sgd (or, if oracle/_ref is absent, the C oracle port) on one core."""
+    import oracle
+    mu = float(ts.global_mean)
+    try:
+        ref = oracle.import_reference()
+        rts, kept = reference_trainset(ref, ts, n_ratings)
+        algo = ref.SVD(n_factors=N_FACTORS, n_epochs=n_epochs, random_state=SEED)
+        ref.AlgoBase.fit(algo, rts)
+        t0 = time.perf_counter()
+        algo.sgd(rts)
+        dt = time.perf_counter() - t0
+        return kept * n_epochs / dt, dt, "reference", kept
+    except ImportError:
+        kept = min(n_ratings, len(rr))
+        t0 = time.perf_counter()
+        oracle.svd_sgd(uu[:kept], ii[:kept], rr[:kept], pu0, qi0, n_epochs, True, mu, *([.005] * 4), *([.02] * 4))
+        dt = time.perf_counter() - t0
+        return kept * n_epochs / dt, dt, "port", kept
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ts, uu, ii, rr, pu0, qi0, _ = load_workload()
+    # one step = one epoch of the reference's SVD.sgd over a bounded prefix of the trainset; sized for ~200 s total
+    budget_s, est_us_per_update = 200.0, 5.0
+    n_keep = int(min(ts.n_ratings, budget_s / max(1, args.steps + args.warmup) / (est_us_per_update * 1e-6)))
+    n_keep = max(n_keep, 20_000)
+    import oracle
+    mu = float(ts.global_mean)
+    try:
+        ref = oracle.import_reference()
+        rts, kept = reference_trainset(ref, ts, n_keep)
+        algo = ref.SVD(n_factors=N_FACTORS, n_epochs=1, random_state=SEED)
+        ref.AlgoBase.fit(algo, rts)
+        step = lambda: algo.sgd(rts)
+        kind = "reference"
+    except ImportError:
+        kept = n_keep
+        step = lambda: oracle.svd_sgd(uu[:kept], ii[:kept], rr[:kept], pu0, qi0, 1, True, mu, *([.005] * 4),
+                                      *([.02] * 4))
+        kind = "port"
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = kept * args.steps / dt
+    sample = "1 epoch of SVD.sgd over the first %d of 1M ratings (all_ratings order) per step" % kept
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from surprise_b200 import _native as nat
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- surprise_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = nat.lib()
+    ts, uu, ii, rr, pu0, qi0, test = load_workload()
+    mu = float(ts.global_mean)
+    n, nu, ni, f = len(rr), ts.n_users, ts.n_items, N_FACTORS
+    updates_per_step = n * N_EPOCHS
+    prm = sgd_params(nat, mu)
+    stream = nat.stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernel_ms = []
+    result = {}
+    if world == 1:
+        d_u, d_i, d_r = nat.to_dev(uu, np.int32), nat.to_dev(ii, np.int32), nat.to_dev(rr, np.float64)
+        d_pu0, d_qi0 = nat.to_dev(pu0, np.float64), nat.to_dev(qi0, np.float64)
+        d_pu, d_qi = torch.empty_like(d_pu0), torch.empty_like(d_qi0)
+        d_bu = nat.empty_dev((nu,), np.float64)
+        d_bi = nat.empty_dev((ni,), np.float64)
+
+        def step(record):
+            # everything SVD.sgd does, inputs resident in HBM: stratify, 20 epochs, factors back as float64
+            plan = C.c_void_p()
+            nat.check(lib.sb2_svd_plan_create_dev(nu, ni, n, nat.ptr(d_u), nat.ptr(d_i), nat.ptr(d_r), C.byref(prm), 0,
+                                                  None, None, stream, C.byref(plan)))
+            nat.check(lib.sb2_svd_plan_reset_dev(plan, nat.ptr(d_pu0), nat.ptr(d_qi0), None, stream))
+            e0, e1 = ev(), ev()
+            e0.record()
+            nat.check(lib.sb2_svd_plan_run(plan, N_EPOCHS, stream))
+            e1.record()
+            nat.check(lib.sb2_svd_plan_read_dev(plan, nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_bu), nat.ptr(d_bi), None,
+                                                stream))
+            torch.cuda.synchronize()
+            lib.sb2_svd_plan_destroy(plan)
+            if record:
+                kernel_ms.append(e0.elapsed_time(e1))
+        ring = None
+    else:
+        from surprise_b200.distributed import RingSVD
+        ring = RingSVD(dist, uu, ii, rr, nu, ni, prm)
+
+        def step(record):
+            ring.reset(pu0, qi0)
+            e0, e1 = ev(), ev()
+            e0.record()
+            ring.run(N_EPOCHS)
+            e1.record()
+            torch.cuda.synchronize()
+            if record:
+                kernel_ms.append(e0.elapsed_time(e1))
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step(False)
+    lib.sb2_reset_launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    e_beg, e_end = ev(), ev()
+    e_beg.record()
+    for _ in range(args.steps):
+        flush.zero_()           # L2 flush (256 MiB > 126 MB L2) between timed iterations, inside the timed region
+        step(True)
+    e_end.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = e_beg.elapsed_time(e_end)
+    launches = int(lib.sb2_launch_count()) + args.steps  # + the flush memset per step
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = updates_per_step * args.steps / (dev_ms * 1e-3)
+
+    # held-out RMSE of the last fit (not timed): parity evidence next to the throughput
+    if world == 1:
+        pu, qi, bu, bi = d_pu.cpu().numpy(), d_qi.cpu().numpy(), d_bu.cpu().numpy(), d_bi.cpu().numpy()
+    else:
+        pu, qi, bu, bi = ring.gather()
+    tu, ti, tr = test
+    est = np.empty(len(tu)); imp = np.empty(len(tu), dtype=np.uint8)
+    tu, ti = np.ascontiguousarray(tu), np.ascontiguousarray(ti)
+    nat.check(lib.sb2_mf_predict(len(tu), nat.hptr(tu), nat.hptr(ti), nu, ni, f, 1, mu, nat.hptr(pu), nat.hptr(qi),
+                                 nat.hptr(bu), nat.hptr(bi), None, None, None, nat.hptr(est), nat.hptr(imp)))
+    rmse = float(np.sqrt(np.mean((np.clip(est, 1, 5) - tr) ** 2)))
+
+    # e2e: host buffers through the C-ABI (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if world == 1:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_u, h_i, h_r = pin(uu), pin(ii), pin(rr)
+        h_pu, h_qi = pin(pu0), pin(qi0)
+        h_bu, h_bi = torch.empty(nu, dtype=torch.float64).pin_memory(), torch.empty(ni, dtype=torch.float64).pin_memory()
+        hp = lambda t_: C.c_void_p(t_.data_ptr())
+        pu_init, qi_init = torch.from_numpy(pu0.copy()), torch.from_numpy(qi0.copy())
+
+        def e2e_step():
+            h_pu.copy_(pu_init); h_qi.copy_(qi_init)   # host-side restore of the in/out buffers (not GPU work)
+            nat.check(lib.sb2_svd_fit(nu, ni, n, hp(h_u), hp(h_i), hp(h_r), C.byref(prm), hp(h_pu), hp(h_qi), hp(h_bu),
+                                      hp(h_bi)))
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        k2 = max(1, min(args.steps, 5))
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(k2):
+            flush.zero_()
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t1
+        h2d = uu.nbytes + ii.nbytes + rr.nbytes + pu0.nbytes + qi0.nbytes
+        d2h = pu0.nbytes + qi0.nbytes + 8 * (nu + ni)
+        e2e = {"value": updates_per_step * k2 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": k2, "ms_per_step": 1e3 * dt / k2,
+               "api": "sb2_svd_fit (host-buffer C-ABI, pinned numpy arrays)"}
+    else:
+        e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "multi-GPU e2e not separately measured; value repeated"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_update = 2 * (2 * f + 2) * 4 + 12
+    k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
+    achieved = bytes_per_update * updates_per_step / (k_ms * 1e-3) / 1e9 if k_ms else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("dsgd_svd_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "dsgd_svd_kernel (20 epochs per launch)" if world == 1 else "ring of dsgd_svd_kernel launches",
+                "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_update": bytes_per_update,
+                "note": "working set (pu+qi fp32 = 3.9 MB) is L2/SMEM resident: the kernel is bound by the stratum "
+                        "hand-off chain, not by HBM; see DESIGN.md"}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, kind, kept = cpu_sgd_rate(ts, uu, ii, rr, pu0, qi0, ts.n_ratings, 3)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+               "sample": "3 epochs of SVD.sgd over %d of the 1M ratings (same factors / hyper-parameters)" % kept}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "256 MiB memset between timed steps (inside the timed region)",
+                       "step": "one full fit = 20 epochs = 2e7 rating updates", "parallelism": "dsgd-ring%d" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "heldout_rmse": rmse, "wall_ms_per_step": wall_ms / args.steps}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,12 +138,25 @@ int sb2_svd_plan_create(int64_t n_users, int64_t n_items, int64_t n, const int32
                         sb2_svd_plan** out);
 int sb2_svd_plan_reset(sb2_svd_plan* plan, const double* pu_host, const double* qi_host,
                        const double* yj_host);
+/* device-pointer forms of create / reset / read (u_ptr / ui_idx: ur CSR, only read when with_yj) */
+int sb2_svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
+                            const int32_t* ui_idx, void* stream, sb2_svd_plan** out);
+int sb2_svd_plan_reset_dev(sb2_svd_plan* plan, const double* pu, const double* qi, const double* yj,
+                           void* stream);
+int sb2_svd_plan_read_dev(sb2_svd_plan* plan, double* pu, double* qi, double* bu, double* bi, double* yj,
+                          void* stream);
 int sb2_svd_plan_run(sb2_svd_plan* plan, int n_epochs, void* stream); /* async on stream */
 int sb2_svd_plan_read(sb2_svd_plan* plan, double* pu, double* qi, double* bu, double* bi, double* yj);
 void sb2_svd_plan_destroy(sb2_svd_plan* plan);
 /* algorithmic bytes per rating update of the plan's kernel (2*(2f+2)*4 + 12 for SVD) */
 int64_t sb2_svd_plan_bytes_per_update(const sb2_svd_plan* plan);
 int sb2_svd_plan_grid(const sb2_svd_plan* plan, int* n_blocks, int* n_sub);
+/* Multi-GPU ring (DSGD across ranks): run the plan on caller-owned fp32 DEVICE factor buffers laid out
+ * rows x sb2_svd_plan_stride() (n_factors rounded up to 4, zero padded); the item-side buffers are the
+ * block that rotates rank -> rank between sub-epochs. */
+int sb2_svd_plan_bind_dev(sb2_svd_plan* plan, float* pu, float* qi, float* bu, float* bi);
+int sb2_svd_plan_stride(const sb2_svd_plan* plan);
 
 /* SVD++.  Replaces SVDpp.sgd, matrix_factorization.pyx:420-504.  yj (n_items x f) in/out like qi.
  * u_ptr / ui_idx: the ur CSR (I_u).  See DESIGN.md for the per-user batching of the y_j update. */

@@ -52,11 +52,16 @@ SIGNATURES = {
     "sb2_svd_fit": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_svd_plan_create": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp]),
     "sb2_svd_plan_reset": (_int, [_vp, _vp, _vp, _vp]),
+    "sb2_svd_plan_create_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "sb2_svd_plan_reset_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "sb2_svd_plan_read_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_svd_plan_run": (_int, [_vp, _int, _vp]),
     "sb2_svd_plan_read": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_svd_plan_destroy": (None, [_vp]),
     "sb2_svd_plan_bytes_per_update": (_i64, [_vp]),
     "sb2_svd_plan_grid": (_int, [_vp, _vp, _vp]),
+    "sb2_svd_plan_bind_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "sb2_svd_plan_stride": (_int, [_vp]),
     "sb2_svdpp_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_svdpp_fit": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_nmf_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

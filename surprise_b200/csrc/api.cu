@@ -62,6 +62,8 @@ int svd_plan_read_dev(sb2_svd_plan* p, double* pu, double* qi, double* bu, doubl
 void svd_plan_destroy(sb2_svd_plan* p);
 int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p);
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w);
+void svd_plan_bind(sb2_svd_plan* p, float* pu, float* qi, float* bu, float* bi);
+int svd_plan_stride(const sb2_svd_plan* p);
 void svd_plan_dims(const sb2_svd_plan* p, int64_t* n_users, int64_t* n_items, int* f, int* with_yj);
 
 static int ensure_device() {
@@ -340,6 +342,20 @@ int sb2_svd_plan_reset(sb2_svd_plan* plan, const double* pu_host, const double* 
     return SB2_OK;
 }
 
+int sb2_svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
+                            const int32_t* ui_idx, void* stream, sb2_svd_plan** out) {
+    SB2_TRY(ensure_device());
+    return svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, with_yj, u_ptr, ui_idx, (cudaStream_t)stream, out);
+}
+int sb2_svd_plan_reset_dev(sb2_svd_plan* plan, const double* pu, const double* qi, const double* yj, void* stream) {
+    return svd_plan_reset_dev(plan, pu, qi, yj, (cudaStream_t)stream);
+}
+int sb2_svd_plan_read_dev(sb2_svd_plan* plan, double* pu, double* qi, double* bu, double* bi, double* yj,
+                          void* stream) {
+    return svd_plan_read_dev(plan, pu, qi, bu, bi, yj, (cudaStream_t)stream);
+}
+
 int sb2_svd_plan_run(sb2_svd_plan* plan, int n_epochs, void* stream) {
     return svd_plan_run(plan, n_epochs, (cudaStream_t)stream);
 }
@@ -368,6 +384,15 @@ int sb2_svd_plan_read(sb2_svd_plan* plan, double* pu, double* qi, double* bu, do
 
 void sb2_svd_plan_destroy(sb2_svd_plan* plan) { svd_plan_destroy(plan); }
 int64_t sb2_svd_plan_bytes_per_update(const sb2_svd_plan* plan) { return svd_plan_bytes_per_update(plan); }
+int sb2_svd_plan_bind_dev(sb2_svd_plan* plan, float* pu, float* qi, float* bu, float* bi) {
+    if (!plan || !pu || !qi || !bu || !bi) {
+        set_error("svd_plan_bind: null argument");
+        return SB2_ERR_INVALID;
+    }
+    svd_plan_bind(plan, pu, qi, bu, bi);
+    return SB2_OK;
+}
+int sb2_svd_plan_stride(const sb2_svd_plan* plan) { return svd_plan_stride(plan); }
 int sb2_svd_plan_grid(const sb2_svd_plan* plan, int* n_blocks, int* n_sub) {
     svd_plan_grid(plan, n_blocks, n_sub);
     return SB2_OK;

@@ -269,8 +269,7 @@ struct sb2_svd_plan {
     size_t smem = 0;
     int *ul = nullptr, *il = nullptr, *off = nullptr, *flags = nullptr;
     float *r = nullptr, *pu = nullptr, *qi = nullptr, *bu = nullptr, *bi = nullptr;
-    double* stage64 = nullptr;  // upload / download staging
-    size_t stage64_elems = 0;
+    bool owns_factors = true;
 };
 
 namespace sb2 {
@@ -297,7 +296,7 @@ static int dsgd_launch_g(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t 
 static void plan_free(sb2_svd_plan* p) {
     if (!p) return;
     cudaFree(p->ul); cudaFree(p->il); cudaFree(p->off); cudaFree(p->flags); cudaFree(p->r);
-    cudaFree(p->pu); cudaFree(p->qi); cudaFree(p->bu); cudaFree(p->bi); cudaFree(p->stage64);
+    if (p->owns_factors) { cudaFree(p->pu); cudaFree(p->qi); cudaFree(p->bu); cudaFree(p->bi); }
     delete p;
 }
 
@@ -321,7 +320,11 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     p->G = F4 <= 4 ? 4 : F4 <= 8 ? 8 : F4 <= 16 ? 16 : 32;
     p->W = p->G == 32 ? 8 : 16;
     if (p->W * p->G > 256) p->W = 256 / p->G;
+    // one CTA per SM, but keep >= ~32 ratings per (user block, item block) so that a stratum's work is
+    // not dwarfed by its hand-off latency (matters for the small sub-matrices of the multi-GPU ring)
     int B = sm_count();
+    const int b_work = std::max(8, (int)sqrt((double)std::max<int64_t>(n, 1) / 32.0));
+    if (B > b_work) B = b_work;
     if (B > n_users) B = (int)n_users;
     if (B > n_items) B = (int)n_items;
     p->B = B;
@@ -355,8 +358,6 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     PLAN_CUDA(cudaMalloc(&p->qi, (size_t)n_items * p->FP * 4));
     PLAN_CUDA(cudaMalloc(&p->bu, (size_t)n_users * 4));
     PLAN_CUDA(cudaMalloc(&p->bi, (size_t)n_items * 4));
-    p->stage64_elems = (size_t)std::max(n_users, n_items) * f;
-    PLAN_CUDA(cudaMalloc(&p->stage64, p->stage64_elems * 8));
 
     // stratify: key -> stable radix sort -> gather records -> offsets
     unsigned *key = nullptr, *key2 = nullptr;
@@ -471,6 +472,14 @@ int svd_plan_read_dev(sb2_svd_plan* p, double* pu, double* qi, double* bu, doubl
 }
 
 void svd_plan_destroy(sb2_svd_plan* p) { plan_free(p); }
+// Use caller-owned fp32 factor buffers (rows x FP, FP = n_factors rounded up to 4): the multi-GPU ring
+// keeps one user block and a rotating item block per rank in torch tensors and binds them per sub-epoch.
+void svd_plan_bind(sb2_svd_plan* p, float* pu, float* qi, float* bu, float* bi) {
+    if (p->owns_factors) { cudaFree(p->pu); cudaFree(p->qi); cudaFree(p->bu); cudaFree(p->bi); }
+    p->owns_factors = false;
+    p->pu = pu; p->qi = qi; p->bu = bu; p->bi = bi;
+}
+int svd_plan_stride(const sb2_svd_plan* p) { return p->FP; }
 // algorithmic bytes per rating update: read + write pu[u], qi[i], bu[u], bi[i] at fp32 + (u, i, r)
 int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p) { return 2ll * (2ll * p->prm.n_factors + 2) * 4 + 12; }
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w) {

@@ -1,0 +1,149 @@
+"""Multi-GPU stratified SGD for SVD: one process per GPU, item blocks rotating rank -> rank.
+
+With P ranks, user u belongs to rank u % P (local row u // P) and item i to item super-block i % P
+(local row i // P).  An epoch is P sub-epochs; in sub-epoch S rank g runs the single-GPU stratified
+kernel over the ratings whose user it owns and whose item lies in super-block (g + S) % P, then hands
+that super-block's (qi, bi) rows to rank g - 1 and receives the next one from rank g + 1
+(torch.distributed P2P: NCCL over NVLink on GPUs, gloo in the CPU tests).  The user rows never move.
+This is the rank-level repetition of the CTA-level ring inside the kernel (csrc/sgd.cu).
+
+``run_block(sb, pu, bu, qi, bi)`` is the unit of work of one sub-epoch; the product passes a closure
+over sb2_svd_plan_run, the CPU tests pass a host function so that the partitioning / rotation logic is
+covered without a GPU.
+"""
+import numpy as np
+
+
+def partition(u, i, r, rank, world):
+    """Ratings owned by `rank`, split by item super-block.  Returns list over sb of (u_local, i_local, r)."""
+    mine = (u % world) == rank
+    um, im, rm = u[mine], i[mine], r[mine]
+    out = []
+    for sb in range(world):
+        sel = (im % world) == sb
+        out.append(((um[sel] // world).astype(np.int32), (im[sel] // world).astype(np.int32), rm[sel]))
+    return out
+
+
+def local_rows(n, part, world):
+    """number of ids in [0, n) congruent to part mod world"""
+    return (n - part + world - 1) // world
+
+
+def ring_epochs(rank, world, n_epochs, held_sb, run_block, exchange):
+    """The rotation schedule.  held_sb: super-block this rank holds at entry (== rank).  `exchange()` sends
+    the held item block to rank-1 and receives from rank+1 (in place)."""
+    sb = held_sb
+    for _ in range(n_epochs):
+        for _s in range(world):
+            run_block(sb)
+            if world > 1:
+                exchange()
+                sb = (sb + 1) % world
+    return sb
+
+
+def make_exchange(dist, rank, world, tensors, scratch):
+    """P2P rotation of the item-side tensors: send to rank-1, receive from rank+1."""
+    dst, src = (rank - 1) % world, (rank + 1) % world
+
+    def exchange():
+        ops = []
+        for t, s in zip(tensors, scratch):
+            ops.append(dist.P2POp(dist.isend, t, dst))
+            ops.append(dist.P2POp(dist.irecv, s, src))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for t, s in zip(tensors, scratch):
+            t.copy_(s)
+    return exchange
+
+
+class RingSVD(object):
+    """SVD fit sharded over the ranks of an initialised torch.distributed group (see module docstring).
+
+    u, i, r: the all_ratings() COO on the host (every rank passes the same arrays); prm: _native.SgdParams.
+    world == 1 degenerates to the single-GPU plan."""
+
+    def __init__(self, dist, u, i, r, n_users, n_items, prm):
+        import ctypes as C
+        from . import _native as nat
+        self.nat, self.C, self.dist = nat, C, dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.n_users, self.n_items, self.prm = n_users, n_items, prm
+        self.f = prm.n_factors
+        P, g = self.world, self.rank
+        self.nu_loc = local_rows(n_users, g, P)
+        self.ni_loc = [local_rows(n_items, sb, P) for sb in range(P)]
+        self.n_local = 0
+        self.plans = []
+        for sb, (ul, il, rl) in enumerate(partition(np.asarray(u), np.asarray(i), np.asarray(r), g, P)):
+            ul, il = np.ascontiguousarray(ul), np.ascontiguousarray(il)
+            rl = np.ascontiguousarray(rl, dtype=np.float64)
+            plan = C.c_void_p()
+            nat.check(nat.lib().sb2_svd_plan_create(self.nu_loc, self.ni_loc[sb], len(rl), nat.hptr(ul), nat.hptr(il),
+                                                    nat.hptr(rl), C.byref(prm), 0, C.byref(plan)))
+            self.plans.append(plan)
+            self.n_local += len(rl)
+        torch = nat.torch_cuda()
+        self.FP = nat.lib().sb2_svd_plan_stride(self.plans[0])
+        dev = nat.device()
+        ni_max = max(self.ni_loc)
+        self.pu = torch.zeros((self.nu_loc, self.FP), dtype=torch.float32, device=dev)
+        self.bu = torch.zeros((self.nu_loc,), dtype=torch.float32, device=dev)
+        self.qi = torch.zeros((ni_max, self.FP), dtype=torch.float32, device=dev)
+        self.bi = torch.zeros((ni_max,), dtype=torch.float32, device=dev)
+        self._scratch = (torch.zeros_like(self.qi), torch.zeros_like(self.bi))
+        self._exchange = (make_exchange(dist, g, P, (self.qi, self.bi), self._scratch) if P > 1 else (lambda: None))
+        self.held = g
+
+    def reset(self, pu0, qi0):
+        """pu0 / qi0: full float64 host (or device) init matrices; each rank keeps its rows."""
+        torch = self.nat.torch_cuda()
+        P, g = self.world, self.rank
+        pu0 = torch.as_tensor(pu0)[g::P].to(self.pu.device, dtype=torch.float32)
+        qi0 = torch.as_tensor(qi0)[g::P].to(self.pu.device, dtype=torch.float32)
+        self.pu.zero_(); self.qi.zero_(); self.bu.zero_(); self.bi.zero_()
+        self.pu[:, :self.f] = pu0
+        self.qi[:qi0.shape[0], :self.f] = qi0
+        self.held = g
+
+    def _run_block(self, sb):
+        nat = self.nat
+        lib = nat.lib()
+        nat.check(lib.sb2_svd_plan_bind_dev(self.plans[sb], nat.ptr(self.pu), nat.ptr(self.qi), nat.ptr(self.bu),
+                                            nat.ptr(self.bi)))
+        nat.check(lib.sb2_svd_plan_run(self.plans[sb], 1, nat.stream()))
+
+    def run(self, n_epochs):
+        self.held = ring_epochs(self.rank, self.world, n_epochs, self.held, self._run_block, self._exchange)
+
+    def gather(self):
+        """Full (pu, qi, bu, bi) float64 numpy arrays on every rank."""
+        torch = self.nat.torch_cuda()
+        P = self.world
+        assert self.held == self.rank
+        ni_max = max(self.ni_loc)
+        nu_max = local_rows(self.n_users, 0, P)
+        outs = []
+        for t, n_max, n_tot in ((self.pu, nu_max, self.n_users), (self.qi, ni_max, self.n_items),
+                                (self.bu, nu_max, self.n_users), (self.bi, ni_max, self.n_items)):
+            pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[:min(t.shape[0], n_max)] = t[:n_max]
+            if P > 1:
+                parts = [torch.zeros_like(pad) for _ in range(P)]
+                self.dist.all_gather(parts, pad)
+            else:
+                parts = [pad]
+            full = torch.zeros((n_tot,) + tuple(t.shape[1:]), dtype=torch.float64, device=t.device)
+            for p in range(P):
+                rows = local_rows(n_tot, p, P)
+                full[p::P] = parts[p][:rows].double()
+            outs.append(full[..., :self.f].cpu().numpy() if full.dim() == 2 else full.cpu().numpy())
+        return tuple(outs)
+
+    def close(self):
+        for p in self.plans:
+            self.nat.lib().sb2_svd_plan_destroy(p)
+        self.plans = []

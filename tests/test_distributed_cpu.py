@@ -1,0 +1,111 @@
+"""world_size-2 gloo test of the multi-GPU SVD ring's host logic (partitioning, rotation schedule, P2P
+exchange).  The per-block unit of work is injected: here it is the oracle's sequential SGD on the block, so
+the 2-process run must equal a single-process replay of the same schedule bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from surprise_b200 import distributed as D  # noqa: E402
+from surprise_b200 import synth  # noqa: E402
+
+F, EPOCHS, WORLD = 6, 2, 2
+HP = dict(lr=.005, reg=.02)
+
+
+def _data():
+    d = synth.ratings(60, 40, 900, seed=4)
+    u, i, r = d["train"]
+    rng = np.random.RandomState(0)
+    return u, i, r, d["n_users"], d["n_items"], rng.normal(0, .1, (d["n_users"], F)), rng.normal(0, .1, (d["n_items"], F))
+
+
+def _block_update(ul, il, rl, pu, bu, qi, bi, mu):
+    import oracle
+    # oracle.svd_sgd starts biases at zero; run one epoch "continuing" by folding biases through a tiny wrapper
+    import ctypes as C
+    lib = oracle.lib()
+    d = C.c_double
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    lib.orc_svd_sgd(C.c_int64(len(rl)), C.c_int(F), p(ul, C.c_int32), p(il, C.c_int32), p(rl, C.c_double), C.c_int(1),
+                    C.c_int(1), d(mu), d(HP["lr"]), d(HP["lr"]), d(HP["lr"]), d(HP["lr"]), d(HP["reg"]), d(HP["reg"]),
+                    d(HP["reg"]), d(HP["reg"]), p(pu, C.c_double), p(qi, C.c_double), p(bu, C.c_double), p(bi, C.c_double))
+
+
+def _replay():
+    u, i, r, nu, ni, pu0, qi0 = _data()
+    mu = float(np.mean(r))
+    parts = [D.partition(u, i, r, g, WORLD) for g in range(WORLD)]
+    pu = [np.ascontiguousarray(pu0[g::WORLD]) for g in range(WORLD)]
+    bu = [np.zeros(len(p)) for p in pu]
+    qi = [np.ascontiguousarray(qi0[s::WORLD]) for s in range(WORLD)]
+    bi = [np.zeros(len(q)) for q in qi]
+    for _ in range(EPOCHS):
+        for S in range(WORLD):
+            for g in range(WORLD):
+                sb = (g + S) % WORLD
+                ul, il, rl = parts[g][sb]
+                _block_update(np.ascontiguousarray(ul), np.ascontiguousarray(il), np.ascontiguousarray(rl), pu[g],
+                              bu[g], qi[sb], bi[sb], mu)
+    return pu, bu, qi, bi
+
+
+def _worker(rank, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    u, i, r, nu, ni, pu0, qi0 = _data()
+    mu = float(np.mean(r))
+    parts = D.partition(u, i, r, rank, WORLD)
+    ni_max = D.local_rows(ni, 0, WORLD)
+    pu = torch.from_numpy(np.ascontiguousarray(pu0[rank::WORLD]).copy())
+    bu = torch.zeros(pu.shape[0], dtype=torch.float64)
+    qi = torch.zeros((ni_max, F), dtype=torch.float64)
+    bi = torch.zeros(ni_max, dtype=torch.float64)
+    mine = qi0[rank::WORLD]
+    qi[:len(mine)] = torch.from_numpy(mine.copy())
+    scratch = (torch.zeros_like(qi), torch.zeros_like(bi))
+    exchange = D.make_exchange(dist, rank, WORLD, (qi, bi), scratch)
+
+    def run_block(sb):
+        ul, il, rl = parts[sb]
+        rows = D.local_rows(ni, sb, WORLD)
+        q = np.ascontiguousarray(qi.numpy()[:rows]); b = np.ascontiguousarray(bi.numpy()[:rows])
+        _block_update(np.ascontiguousarray(ul), np.ascontiguousarray(il), np.ascontiguousarray(rl), pu.numpy(),
+                      bu.numpy(), q, b, mu)
+        qi[:rows] = torch.from_numpy(q); bi[:rows] = torch.from_numpy(b)
+
+    held = D.ring_epochs(rank, WORLD, EPOCHS, rank, run_block, exchange)
+    assert held == rank
+    rows = D.local_rows(ni, rank, WORLD)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), pu=pu.numpy(), bu=bu.numpy(), qi=qi.numpy()[:rows],
+             bi=bi.numpy()[:rows])
+    dist.destroy_process_group()
+
+
+def test_partition_covers_every_rating_once():
+    u, i, r, nu, ni, _, _ = _data()
+    seen = 0
+    for g in range(3):
+        for sb, (ul, il, rl) in enumerate(D.partition(u, i, r, g, 3)):
+            seen += len(rl)
+            assert np.all(ul < D.local_rows(nu, g, 3)) and np.all(il < D.local_rows(ni, sb, 3))
+    assert seen == len(r)
+    assert sum(D.local_rows(nu, g, 3) for g in range(3)) == nu
+
+
+def test_ring_two_ranks_equals_replay(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    pu, bu, qi, bi = _replay()
+    for g in range(WORLD):
+        got = np.load(os.path.join(str(tmp_path), "r%d.npz" % g))
+        assert np.array_equal(got["pu"], pu[g]) and np.array_equal(got["bu"], bu[g])
+        assert np.array_equal(got["qi"], qi[g]) and np.array_equal(got["bi"], bi[g])

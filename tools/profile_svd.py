@@ -1,0 +1,30 @@
+"""One SVD fit of the bench workload (for ncu)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import bench  # noqa: E402
+from surprise_b200 import _native as nat  # noqa: E402
+
+ts, uu, ii, rr, pu0, qi0, test = bench.load_workload()
+prm = bench.sgd_params(nat, float(ts.global_mean))
+lib = nat.lib()
+plan = C.c_void_p()
+nat.check(lib.sb2_svd_plan_create(ts.n_users, ts.n_items, len(rr), nat.hptr(uu), nat.hptr(ii), nat.hptr(rr), C.byref(prm),
+                                  0, C.byref(plan)))
+for it in range(2):
+    nat.check(lib.sb2_svd_plan_reset(plan, nat.hptr(pu0), nat.hptr(qi0), None))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nat.check(lib.sb2_svd_plan_run(plan, 20, nat.stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    print("dsgd kernel 20 epochs: %.3f ms -> %.1f M updates/s" % (e0.elapsed_time(e1), 2e7 / e0.elapsed_time(e1) / 1e3))
+b, w = C.c_int(), C.c_int()
+lib.sb2_svd_plan_grid(plan, C.byref(b), C.byref(w))
+print("grid B=%d W=%d" % (b.value, w.value))
+lib.sb2_svd_plan_destroy(plan)
