@@ -226,11 +226,15 @@ def run_ours(args):
         d_bu = nat.empty_dev((nu,), np.float64)
         d_bi = nat.empty_dev((ni,), np.float64)
 
+        dbg = os.environ.get("BENCH_DEBUG")
+
         def step(record):
             # everything SVD.sgd does, inputs resident in HBM: stratify, 20 epochs, factors back as float64
             plan = C.c_void_p()
+            ta = time.perf_counter()
             nat.check(lib.sb2_svd_plan_create_dev(nu, ni, n, nat.ptr(d_u), nat.ptr(d_i), nat.ptr(d_r), C.byref(prm), 0,
                                                   None, None, stream, C.byref(plan)))
+            tb = time.perf_counter()
             nat.check(lib.sb2_svd_plan_reset_dev(plan, nat.ptr(d_pu0), nat.ptr(d_qi0), None, stream))
             e0, e1 = ev(), ev()
             e0.record()
@@ -239,7 +243,11 @@ def run_ours(args):
             nat.check(lib.sb2_svd_plan_read_dev(plan, nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_bu), nat.ptr(d_bi), None,
                                                 stream))
             torch.cuda.synchronize()
+            tc = time.perf_counter()
             lib.sb2_svd_plan_destroy(plan)
+            if dbg:
+                print("step phases ms: create %.2f run+read %.2f destroy %.2f" % (
+                    (tb - ta) * 1e3, (tc - tb) * 1e3, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
             if record:
                 kernel_ms.append(e0.elapsed_time(e1))
         ring = None
@@ -261,7 +269,7 @@ def run_ours(args):
         flush.zero_()
         step(False)
     lib.sb2_reset_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
     if sampler:
         sampler.start()
     barrier()

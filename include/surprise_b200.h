@@ -157,6 +157,10 @@ int sb2_svd_plan_grid(const sb2_svd_plan* plan, int* n_blocks, int* n_sub);
  * block that rotates rank -> rank between sub-epochs. */
 int sb2_svd_plan_bind_dev(sb2_svd_plan* plan, float* pu, float* qi, float* bu, float* bi);
 int sb2_svd_plan_stride(const sb2_svd_plan* plan);
+/* Per-CTA counters of the last run, cycles_host[n_blocks][8] (n_blocks from sb2_svd_plan_grid): SM cycles in
+ * {ring wait, item-block load, rating updates, write-back, lane-group-0 updates}, then the number of
+ * lane-group-0 updates, the number of waves, 0. */
+int sb2_svd_plan_profile(const sb2_svd_plan* plan, int64_t* cycles_host);
 
 /* SVD++.  Replaces SVDpp.sgd, matrix_factorization.pyx:420-504.  yj (n_items x f) in/out like qi.
  * u_ptr / ui_idx: the ur CSR (I_u).  See DESIGN.md for the per-user batching of the y_j update. */

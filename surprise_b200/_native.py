@@ -62,6 +62,7 @@ SIGNATURES = {
     "sb2_svd_plan_grid": (_int, [_vp, _vp, _vp]),
     "sb2_svd_plan_bind_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "sb2_svd_plan_stride": (_int, [_vp]),
+    "sb2_svd_plan_profile": (_int, [_vp, _vp]),
     "sb2_svdpp_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_svdpp_fit": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_nmf_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

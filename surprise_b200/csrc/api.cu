@@ -64,6 +64,7 @@ int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p);
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w);
 void svd_plan_bind(sb2_svd_plan* p, float* pu, float* qi, float* bu, float* bi);
 int svd_plan_stride(const sb2_svd_plan* p);
+int svd_plan_profile(const sb2_svd_plan* p, long long* out_host);
 void svd_plan_dims(const sb2_svd_plan* p, int64_t* n_users, int64_t* n_items, int* f, int* with_yj);
 
 static int ensure_device() {
@@ -74,6 +75,19 @@ static int ensure_device() {
                   e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
         cudaGetLastError();
         return SB2_ERR_CUDA;
+    }
+    // Keep stream-ordered allocations cached in the device's default pool instead of returning them to
+    // the OS at every synchronisation (the default release threshold is 0): the similarity path allocates
+    // GBs of panels / planes per call and re-mapping them would dwarf the kernels.
+    static thread_local int pool_ready_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != pool_ready_dev) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_ready_dev = dev;
     }
     return SB2_OK;
 }
@@ -393,6 +407,9 @@ int sb2_svd_plan_bind_dev(sb2_svd_plan* plan, float* pu, float* qi, float* bu, f
     return SB2_OK;
 }
 int sb2_svd_plan_stride(const sb2_svd_plan* plan) { return svd_plan_stride(plan); }
+int sb2_svd_plan_profile(const sb2_svd_plan* plan, int64_t* cycles_host) {
+    return svd_plan_profile(plan, reinterpret_cast<long long*>(cycles_host));
+}
 int sb2_svd_plan_grid(const sb2_svd_plan* plan, int* n_blocks, int* n_sub) {
     svd_plan_grid(plan, n_blocks, n_sub);
     return SB2_OK;

@@ -8,16 +8,22 @@
 // into shared memory, updates, and writes back.  Item blocks move CTA -> CTA along a ring, so instead
 // of a grid-wide barrier per stratum each CTA waits on a per-item-block step counter that its ring
 // neighbour publishes (st.release / ld.acquire) -- every block is touched by exactly one CTA at a time.
-// Inside a block the same construction is repeated across the W lane-groups of the CTA (W x W
-// sub-blocks, W sub-strata separated by __syncthreads()), so no two lane-groups ever hold the same
-// user or item row: the schedule is conflict-free by construction, with no atomics on factors.
+//
+// Inside a (user block, item block) cell the ratings form a bipartite multigraph; a greedy edge
+// colouring (done once, on the device, at plan creation) splits them into "waves": no two ratings of a
+// wave share a user or an item, so the W lane-groups of the CTA process a wave concurrently and
+// waves are separated by __syncthreads().  The number of waves is the cell's maximum degree (up to a
+// factor < 2), i.e. the inherent sequential depth of the cell.  Colours >= 63 (very popular items)
+// fall into a tail that one lane-group replays sequentially.  The schedule is conflict-free by
+// construction: no atomics on factors, and the result is deterministic.
 //
 // One lane-group (G = 4..32 lanes, chosen from n_factors) performs one rating update: 128-bit loads
 // of the pu / qi rows, shuffle-tree dot product, bias update by the group leader, factor update and
 // 128-bit stores.  Arithmetic is fp32 (the contract is held-out RMSE within 0.005 of the reference).
-#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -26,13 +32,17 @@
 
 namespace sb2 {
 
+constexpr int NW = 64;  // waves per cell: 63 colours + 1 sequential tail
+
 struct DsgdArgs {
     int n_users, n_items, B, W, f, FP;  // FP = n_factors rounded up to 4
     int max_ul, max_il;                 // rows per user / item block (ceil)
-    const int* ul;                      // records sorted by (stratum, user block, sub-stratum, user sub-block)
+    int rec_cap;                        // records of a cell staged in shared memory
+    const int* ul;                      // records grouped by cell (stratum-major), colour-sorted inside a cell
     const int* il;
     const float* r;
-    const int* off;                     // B*B*W*W + 1 offsets into the records
+    const int* cell_off;                // B*B + 1 offsets into the records, cell = s * B + user_block
+    const int* wave_off;                // [B*B][NW + 1] wave boundaries relative to the cell start
     float* pu;                          // n_users x FP
     float* qi;                          // n_items x FP
     float* bu;
@@ -40,13 +50,15 @@ struct DsgdArgs {
     int* flags;                         // B step counters (ring hand-off of item blocks)
     float mu, lr_bu, lr_bi, lr_pu, lr_qi, reg_bu, reg_bi, reg_pu, reg_qi;
     int n_epochs;
+    long long* prof;                    // optional: [CTA][8]: cycles in {ring wait, block load, updates, write-back, group-0 updates}, #group-0 updates, #waves, 0
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
+__device__ __forceinline__ int ld_relaxed(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -72,9 +84,86 @@ __device__ __forceinline__ void sc_st(float* p, float v) {
     else __stcg(p, v);
 }
 
+// one rating update by a group of G lanes (all lanes hold the same ul / il / r).
+// FAST: n_factors <= 4 * G, one 128-bit chunk per lane, the rows stay in registers between the dot
+// product and the update.  Otherwise lanes stride over the chunks and re-read the rows.
+template <int G, bool FAST, bool SU, bool SI, bool BIASED>
+__device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float* qrow, float* bup, float* bip, float r,
+                                           int gl, unsigned gmask, int F4) {
+    if (FAST) {
+        const bool act = gl < F4;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
+        if (act) {
+            p = row_ld4<SU>(prow + 4 * gl);
+            q = row_ld4<SI>(qrow + 4 * gl);
+        }
+        float b_u = 0.f, b_i = 0.f;
+        if (BIASED) {
+            b_u = sc_ld<SU>(bup);
+            b_i = sc_ld<SI>(bip);
+        }
+        float dot = (p.x * q.x + p.y * q.y) + (p.z * q.z + p.w * q.w);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
+        const float err = BIASED ? r - (a.mu + b_u + b_i + dot) : r - dot;
+        if (act) {
+            float4 pn, qn;
+            pn.x = p.x + a.lr_pu * (err * q.x - a.reg_pu * p.x);
+            pn.y = p.y + a.lr_pu * (err * q.y - a.reg_pu * p.y);
+            pn.z = p.z + a.lr_pu * (err * q.z - a.reg_pu * p.z);
+            pn.w = p.w + a.lr_pu * (err * q.w - a.reg_pu * p.w);
+            qn.x = q.x + a.lr_qi * (err * p.x - a.reg_qi * q.x);
+            qn.y = q.y + a.lr_qi * (err * p.y - a.reg_qi * q.y);
+            qn.z = q.z + a.lr_qi * (err * p.z - a.reg_qi * q.z);
+            qn.w = q.w + a.lr_qi * (err * p.w - a.reg_qi * q.w);
+            row_st4<SU>(prow + 4 * gl, pn);
+            row_st4<SI>(qrow + 4 * gl, qn);
+        }
+        if (BIASED && gl == 0) {
+            sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
+            sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
+        }
+        return;
+    }
+    float dot = 0.f;
+    for (int c = gl; c < F4; c += G) {
+        const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
+        dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
+    float err;
+    if (BIASED) {
+        const float b_u = sc_ld<SU>(bup), b_i = sc_ld<SI>(bip);
+        err = r - (a.mu + b_u + b_i + dot);
+        __syncwarp(gmask);  // every lane has read the biases before the leader overwrites them
+        if (gl == 0) {
+            sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
+            sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
+        }
+    } else {
+        err = r - dot;
+    }
+#pragma unroll 1
+    for (int c = gl; c < F4; c += G) {
+        const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
+        float4 pn, qn;
+        pn.x = p.x + a.lr_pu * (err * q.x - a.reg_pu * p.x);
+        pn.y = p.y + a.lr_pu * (err * q.y - a.reg_pu * p.y);
+        pn.z = p.z + a.lr_pu * (err * q.z - a.reg_pu * p.z);
+        pn.w = p.w + a.lr_pu * (err * q.w - a.reg_pu * p.w);
+        qn.x = q.x + a.lr_qi * (err * p.x - a.reg_qi * q.x);
+        qn.y = q.y + a.lr_qi * (err * p.y - a.reg_qi * q.y);
+        qn.z = q.z + a.lr_qi * (err * p.z - a.reg_qi * q.z);
+        qn.w = q.w + a.lr_qi * (err * p.w - a.reg_qi * q.w);
+        row_st4<SU>(prow + 4 * c, pn);
+        row_st4<SI>(qrow + 4 * c, qn);
+    }
+}
+
 // G lanes per rating, SU / SI: user / item block staged in shared memory, BIASED: SVD(biased=True)
-template <int G, bool SU, bool SI, bool BIASED>
-__global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
+template <int G, bool FAST, bool SU, bool SI, bool BIASED>
+__global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int B = a.B, W = a.W, FP = a.FP, F4 = a.FP >> 2;
     const int ub = blockIdx.x;
@@ -88,114 +177,134 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     float* qi_s = pu_s + (SU ? (size_t)a.max_ul * FP : 0);
     float* bu_s = qi_s + (SI ? (size_t)a.max_il * FP : 0);
     float* bi_s = bu_s + (SU ? a.max_ul : 0);
-    int* off_s = reinterpret_cast<int*>(bi_s + (SI ? a.max_il : 0));
+    int* wave_s = reinterpret_cast<int*>(bi_s + (SI ? a.max_il : 0));
+    int* coff_s = wave_s + (NW + 1);          // [2 * B]: cell begin / end per stratum
+    int* rul_s = coff_s + 2 * B;
+    int* ril_s = rul_s + a.rec_cap;
+    float* rr_s = reinterpret_cast<float*>(ril_s + a.rec_cap);
 
     const int nu_local = (a.n_users - ub + B - 1) / B;
     if (SU) {
-        for (int t = tid; t < nu_local * F4; t += nthr) {
-            const int l = t / F4, c = t % F4;
+        for (int l = tid / F4, c = tid % F4; l < nu_local; ) {
             reinterpret_cast<float4*>(pu_s)[l * F4 + c] =
                 __ldcg(reinterpret_cast<const float4*>(a.pu + ((size_t)(ub + (size_t)l * B)) * FP) + c);
+            c += nthr % F4; l += nthr / F4;
+            if (c >= F4) { c -= F4; ++l; }
         }
         for (int l = tid; l < nu_local; l += nthr) bu_s[l] = __ldcg(a.bu + ub + (size_t)l * B);
     }
+    for (int s = tid; s < B; s += nthr) {
+        coff_s[2 * s] = a.cell_off[(size_t)s * B + ub];
+        coff_s[2 * s + 1] = a.cell_off[(size_t)s * B + ub + 1];
+    }
     __syncthreads();
 
+    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, t_proc = 0, n_proc = 0, n_wave = 0;
     for (int ep = 0; ep < a.n_epochs; ++ep) {
         for (int s = 0; s < B; ++s) {
             const int ib = (ub + s) % B;
             const int step = ep * B + s;
+            const long long c0 = clock64();
+            // this stratum's records and wave table do not depend on the ring: fetch them while waiting
+            const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
+            const int staged = min(cnt, a.rec_cap);
+            for (int t = tid; t < staged; t += nthr) {
+                rul_s[t] = a.ul[k0 + t];
+                ril_s[t] = a.il[k0 + t];
+                rr_s[t] = a.r[k0 + t];
+            }
+            for (int t = tid; t <= NW; t += nthr) wave_s[t] = a.wave_off[((size_t)s * B + ub) * (NW + 1) + t];
             if (tid == 0) {
-                while (ld_acquire(a.flags + ib) != step) { /* ring neighbour still owns the block */ }
+                while (ld_relaxed(a.flags + ib) != step) { /* ring neighbour still owns the block */ }
+                fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
             }
             __syncthreads();
+            const long long c1 = clock64();
             const int ni_local = (a.n_items - ib + B - 1) / B;
             if (SI) {
-                for (int t = tid; t < ni_local * F4; t += nthr) {
-                    const int l = t / F4, c = t % F4;
-                    reinterpret_cast<float4*>(qi_s)[l * F4 + c] =
-                        __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + c);
-                }
-                for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
-            }
-            const int* offg = a.off + ((size_t)s * B + ub) * (size_t)(W * W);
-            for (int t = tid; t <= W * W; t += nthr) off_s[t] = offg[t];
-            __syncthreads();
-
-            for (int t = 0; t < W; ++t) {
-                const int k0 = off_s[t * W + gid], k1 = off_s[t * W + gid + 1];
-                for (int kb = k0; kb < k1; kb += G) {
-                    // the group fetches up to G records at once, then replays them one by one
-                    const int kk = kb + gl;
-                    int my_ul = 0, my_il = 0;
-                    float my_r = 0.f;
-                    if (kk < k1) { my_ul = a.ul[kk]; my_il = a.il[kk]; my_r = a.r[kk]; }
-                    const int cnt = min(G, k1 - kb);
-                    for (int j = 0; j < cnt; ++j) {
-                        const int ul = __shfl_sync(gmask, my_ul, gbase + j);
-                        const int il = __shfl_sync(gmask, my_il, gbase + j);
-                        const float r = __shfl_sync(gmask, my_r, gbase + j);
-                        float* prow = SU ? pu_s + (size_t)ul * FP : a.pu + ((size_t)(ub + (size_t)ul * B)) * FP;
-                        float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
-                        float dot = 0.f;
-                        for (int c = gl; c < F4; c += G) {
-                            const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
-                            dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
-                        }
+                const int total = ni_local * F4;
+                for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
+                    float4 v[4];
 #pragma unroll
-                        for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
-                        float err;
-                        if (BIASED) {
-                            float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
-                            float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
-                            const float b_u = sc_ld<SU>(bup), b_i = sc_ld<SI>(bip);
-                            err = r - (a.mu + b_u + b_i + dot);
-                            if (gl == 0) {
-                                sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
-                                sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
-                            }
-                        } else {
-                            err = r - dot;
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = t0 + j * nthr;
+                        if (t < total) {
+                            const int l = t / F4, c = t - l * F4;
+                            v[j] = __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + c);
                         }
-                        for (int c = gl; c < F4; c += G) {
-                            const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
-                            float4 pn, qn;
-                            pn.x = p.x + a.lr_pu * (err * q.x - a.reg_pu * p.x);
-                            pn.y = p.y + a.lr_pu * (err * q.y - a.reg_pu * p.y);
-                            pn.z = p.z + a.lr_pu * (err * q.z - a.reg_pu * p.z);
-                            pn.w = p.w + a.lr_pu * (err * q.w - a.reg_pu * p.w);
-                            qn.x = q.x + a.lr_qi * (err * p.x - a.reg_qi * q.x);
-                            qn.y = q.y + a.lr_qi * (err * p.y - a.reg_qi * q.y);
-                            qn.z = q.z + a.lr_qi * (err * p.z - a.reg_qi * q.z);
-                            qn.w = q.w + a.lr_qi * (err * p.w - a.reg_qi * q.w);
-                            row_st4<SU>(prow + 4 * c, pn);
-                            row_st4<SI>(qrow + 4 * c, qn);
-                        }
-                        __syncwarp(gmask);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = t0 + j * nthr;
+                        if (t < total) reinterpret_cast<float4*>(qi_s)[t] = v[j];
                     }
                 }
+                for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
                 __syncthreads();
             }
+            const long long c2 = clock64();
 
+            auto process = [&](int k) {
+                int ul, il;
+                float r;
+                if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
+                else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
+                float* prow = SU ? pu_s + (size_t)ul * FP : a.pu + ((size_t)(ub + (size_t)ul * B)) * FP;
+                float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
+                float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
+                float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
+                sgd_update<G, FAST, SU, SI, BIASED>(a, prow, qrow, bup, bip, r, gl, gmask, F4);
+            };
+            for (int w = 0; w < NW - 1; ++w) {
+                const int wb = wave_s[w], we = wave_s[w + 1];
+                if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
+                for (int k = wb + gid; k < we; k += W) {
+                    const long long p0 = clock64();
+                    process(k);
+                    t_proc += clock64() - p0;
+                    ++n_proc;
+                }
+                ++n_wave;
+                __syncthreads();
+            }
+            {
+                const int wb = wave_s[NW - 1], we = wave_s[NW];
+                if (wb != we) {  // sequential tail (colour overflow), one lane-group replays it in order
+                    if (gid == 0)
+                        for (int k = wb; k < we; ++k) {
+                            process(k);
+                            __syncwarp(gmask);  // consecutive tail ratings may share a row
+                        }
+                    __syncthreads();
+                }
+            }
+            const long long c3 = clock64();
             if (SI) {
-                for (int t = tid; t < ni_local * F4; t += nthr) {
-                    const int l = t / F4, c = t % F4;
+                for (int l = tid / F4, c = tid % F4; l < ni_local; ) {
                     __stcg(reinterpret_cast<float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + c,
                            reinterpret_cast<const float4*>(qi_s)[l * F4 + c]);
+                    c += nthr % F4; l += nthr / F4;
+                    if (c >= F4) { c -= F4; ++l; }
                 }
                 if (BIASED)
                     for (int l = tid; l < ni_local; l += nthr) __stcg(a.bi + ib + (size_t)l * B, bi_s[l]);
             }
-            __threadfence();
+            // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
             __syncthreads();
             if (tid == 0) st_release(a.flags + ib, step + 1);
+            t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2; t_wb += clock64() - c3;
         }
     }
+    if (a.prof != nullptr && tid == 0) {
+        a.prof[ub * 8 + 0] = t_wait; a.prof[ub * 8 + 1] = t_load; a.prof[ub * 8 + 2] = t_upd; a.prof[ub * 8 + 3] = t_wb;
+        a.prof[ub * 8 + 4] = t_proc; a.prof[ub * 8 + 5] = n_proc; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = 0;
+    }
     if (SU) {
-        for (int t = tid; t < nu_local * F4; t += nthr) {
-            const int l = t / F4, c = t % F4;
+        for (int l = tid / F4, c = tid % F4; l < nu_local; ) {
             __stcg(reinterpret_cast<float4*>(a.pu + ((size_t)(ub + (size_t)l * B)) * FP) + c,
                    reinterpret_cast<const float4*>(pu_s)[l * F4 + c]);
+            c += nthr % F4; l += nthr / F4;
+            if (c >= F4) { c -= F4; ++l; }
         }
         if (BIASED)
             for (int l = tid; l < nu_local; l += nthr) __stcg(a.bu + ub + (size_t)l * B, bu_s[l]);
@@ -203,38 +312,73 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// preparation kernels
+// preparation kernels: cell key -> stable sort -> per-cell greedy edge colouring -> wave tables
 // ------------------------------------------------------------------------------------------------
-__global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int B, int W,
+__global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int B,
                                 int n_users, int n_items, unsigned* __restrict__ key, int* __restrict__ val,
-                                int* status) {
+                                int* __restrict__ cnt, int* status) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int uu = u[k], ii = i[k];
+    val[k] = (int)k;
     if (uu < 0 || uu >= n_users || ii < 0 || ii >= n_items) {
         atomicExch(status, 1);
         key[k] = 0;
-        val[k] = (int)k;
         return;
     }
     const int ub = uu % B, ibk = ii % B;
-    const int uw = (uu / B) % W, iw = (ii / B) % W;
-    const int s = (ibk - ub + B) % B, t = (iw - uw + W) % W;
-    key[k] = (unsigned)((((size_t)s * B + ub) * W + t) * W + uw);
-    val[k] = (int)k;
+    const int s = (ibk - ub + B) % B;
+    const unsigned cell = (unsigned)(s * B + ub);
+    key[k] = cell;
+    atomicAdd(&cnt[cell], 1);
 }
 
-__global__ void dsgd_gather_kernel(int64_t n, const int* __restrict__ val, const unsigned* __restrict__ key_sorted,
-                                   const int32_t* __restrict__ u, const int32_t* __restrict__ i,
-                                   const double* __restrict__ r, int B, int* __restrict__ ul, int* __restrict__ il,
-                                   float* __restrict__ rr, int* __restrict__ cnt) {
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int src = val[k];
-    ul[k] = u[src] / B;
-    il[k] = i[src] / B;
-    rr[k] = (float)r[src];
-    atomicAdd(&cnt[key_sorted[k]], 1);
+// One warp per cell.  Lane 0 walks the cell's ratings in their (stable) input order and gives each the
+// lowest colour not yet used by its user or its item (64-bit masks in shared memory); colours >= 63
+// share the sequential tail.  Then a counting sort by colour writes the records and the wave table.
+__global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int max_ul, int max_il,
+                                                        const int* __restrict__ cell_off, const int* __restrict__ val,
+                                                        const int32_t* __restrict__ u, const int32_t* __restrict__ i,
+                                                        const double* __restrict__ r, uint8_t* __restrict__ color_tmp,
+                                                        int* __restrict__ ul_out, int* __restrict__ il_out,
+                                                        float* __restrict__ r_out, int* __restrict__ wave_off,
+                                                        int* status) {
+    extern __shared__ unsigned long long masks[];  // [max_ul] user masks, [max_il] item masks
+    __shared__ int hist[NW + 1];
+    const int lane = threadIdx.x;
+    for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        const int k0 = cell_off[cell], k1 = cell_off[cell + 1];
+        for (int t = lane; t < max_ul + max_il; t += 32) masks[t] = 0ull;
+        for (int t = lane; t <= NW; t += 32) hist[t] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            atomicMax(&status[1], k1 - k0);
+            for (int k = k0; k < k1; ++k) {
+                const int src = val[k];
+                const int ul = u[src] / B, il = i[src] / B;
+                const unsigned long long used = masks[ul] | masks[max_ul + il];
+                int c = __ffsll((long long)~used) - 1;  // lowest free colour, -1 if none
+                if (c < 0 || c >= NW - 1) c = NW - 1;
+                else {
+                    masks[ul] |= 1ull << c;
+                    masks[max_ul + il] |= 1ull << c;
+                }
+                color_tmp[k] = (uint8_t)c;
+                hist[c + 1]++;
+            }
+            for (int c = 0; c < NW; ++c) hist[c + 1] += hist[c];
+            for (int c = 0; c <= NW; ++c) wave_off[(size_t)cell * (NW + 1) + c] = hist[c];
+            for (int k = k0; k < k1; ++k) {
+                const int src = val[k];
+                const int c = color_tmp[k];
+                const int pos = k0 + hist[c]++;
+                ul_out[pos] = u[src] / B;
+                il_out[pos] = i[src] / B;
+                r_out[pos] = (float)r[src];
+            }
+        }
+        __syncwarp();
+    }
 }
 
 __global__ void f64_to_rows_kernel(int64_t rows, int f, int FP, const double* __restrict__ src, float* __restrict__ dst) {
@@ -265,18 +409,21 @@ struct sb2_svd_plan {
     int64_t n_users = 0, n_items = 0, n = 0;
     sb2_sgd_params prm;
     int B = 0, W = 0, G = 0, FP = 0;
-    bool stage_u = false, stage_i = false;
+    bool stage_u = false, stage_i = false, fast = true;
     size_t smem = 0;
-    int *ul = nullptr, *il = nullptr, *off = nullptr, *flags = nullptr;
+    int *ul = nullptr, *il = nullptr, *off = nullptr, *wave_off = nullptr, *flags = nullptr;
+    int rec_cap = 0, max_cell = 0;
     float *r = nullptr, *pu = nullptr, *qi = nullptr, *bu = nullptr, *bi = nullptr;
     bool owns_factors = true;
+    cudaStream_t alloc_stream = nullptr;
+    long long* prof = nullptr;
 };
 
 namespace sb2 {
 
-template <int G, bool SU, bool SI, bool BIASED>
+template <int G, bool FAST, bool SU, bool SI, bool BIASED>
 static int dsgd_launch_t(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
-    auto kern = dsgd_svd_kernel<G, SU, SI, BIASED>;
+    auto kern = dsgd_svd_kernel<G, FAST, SU, SI, BIASED>;
     SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     void* args[] = {(void*)&a};
     SB2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(p->B), dim3(p->W * G), args, p->smem, st));
@@ -284,19 +431,27 @@ static int dsgd_launch_t(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t 
     return SB2_OK;
 }
 
-template <int G>
+template <int G, bool FAST>
 static int dsgd_launch_g(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
     const bool b = p->prm.biased != 0;
-    if (p->stage_u && p->stage_i) return b ? dsgd_launch_t<G, true, true, true>(p, a, st) : dsgd_launch_t<G, true, true, false>(p, a, st);
-    if (!p->stage_u && p->stage_i) return b ? dsgd_launch_t<G, false, true, true>(p, a, st) : dsgd_launch_t<G, false, true, false>(p, a, st);
-    if (p->stage_u && !p->stage_i) return b ? dsgd_launch_t<G, true, false, true>(p, a, st) : dsgd_launch_t<G, true, false, false>(p, a, st);
-    return b ? dsgd_launch_t<G, false, false, true>(p, a, st) : dsgd_launch_t<G, false, false, false>(p, a, st);
+    // staging plans: both blocks in shared memory, item block only, or neither
+    if (p->stage_u && p->stage_i)
+        return b ? dsgd_launch_t<G, FAST, true, true, true>(p, a, st) : dsgd_launch_t<G, FAST, true, true, false>(p, a, st);
+    if (p->stage_i)
+        return b ? dsgd_launch_t<G, FAST, false, true, true>(p, a, st) : dsgd_launch_t<G, FAST, false, true, false>(p, a, st);
+    return b ? dsgd_launch_t<G, FAST, false, false, true>(p, a, st) : dsgd_launch_t<G, FAST, false, false, false>(p, a, st);
+}
+
+static void free_async(void* q, cudaStream_t st) {
+    if (q) cudaFreeAsync(q, st);
 }
 
 static void plan_free(sb2_svd_plan* p) {
     if (!p) return;
-    cudaFree(p->ul); cudaFree(p->il); cudaFree(p->off); cudaFree(p->flags); cudaFree(p->r);
-    if (p->owns_factors) { cudaFree(p->pu); cudaFree(p->qi); cudaFree(p->bu); cudaFree(p->bi); }
+    cudaStream_t st = p->alloc_stream;
+    free_async(p->ul, st); free_async(p->il, st); free_async(p->off, st); free_async(p->wave_off, st); free_async(p->flags, st);
+    free_async(p->r, st); free_async(p->prof, st);
+    if (p->owns_factors) { free_async(p->pu, st); free_async(p->qi, st); free_async(p->bu, st); free_async(p->bi, st); }
     delete p;
 }
 
@@ -314,29 +469,35 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     }
     sb2_svd_plan* p = new sb2_svd_plan();
     p->n_users = n_users; p->n_items = n_items; p->n = n; p->prm = *prm;
+    p->alloc_stream = st;
     const int f = prm->n_factors;
     p->FP = (int)round_up(f, 4);
     const int F4 = p->FP / 4;
+    // lanes per rating: the smallest power of two covering the row in 128-bit chunks (one chunk per lane,
+    // rows stay in registers); rows longer than 128 factors fall back to 32 lanes striding the row.
+    p->fast = F4 <= 32;
     p->G = F4 <= 4 ? 4 : F4 <= 8 ? 8 : F4 <= 16 ? 16 : 32;
-    p->W = p->G == 32 ? 8 : 16;
-    if (p->W * p->G > 256) p->W = 256 / p->G;
-    // one CTA per SM, but keep >= ~32 ratings per (user block, item block) so that a stratum's work is
-    // not dwarfed by its hand-off latency (matters for the small sub-matrices of the multi-GPU ring)
+    const int threads = p->fast ? 1024 : 256;
+    p->W = threads / p->G;
+    if (const char* e = getenv("SB2_DSGD_GROUPS")) {
+        const int w = atoi(e);
+        if (w > 0 && w * p->G <= threads && (w * p->G) % 32 == 0) p->W = w;
+    }
+    // Number of blocks B (= CTAs = strata per epoch).  Every stratum pays a fixed ring hand-off latency
+    // (write-back, release, acquire, reload: ~7k cycles measured) on top of its waves, so B trades
+    // parallelism against hand-offs: aim for cells of ~10 waves x W ratings, capped by the SM count.
     int B = sm_count();
-    const int b_work = std::max(8, (int)sqrt((double)std::max<int64_t>(n, 1) / 32.0));
+    const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
     if (B > b_work) B = b_work;
+    if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
+        const int b = atoi(e);
+        if (b > 0 && b <= sm_count()) B = b;
+    }
     if (B > n_users) B = (int)n_users;
     if (B > n_items) B = (int)n_items;
     p->B = B;
     const int max_ul = (int)ceil_div(n_users, B), max_il = (int)ceil_div(n_items, B);
-    // shared-memory staging plan: items first (they move every stratum), then users
-    const size_t off_bytes = (size_t)(p->W * p->W + 1) * sizeof(int) + 16;
-    const size_t need_i = (size_t)max_il * (p->FP + 1) * sizeof(float) + 16;
-    const size_t need_u = (size_t)max_ul * (p->FP + 1) * sizeof(float) + 16;
-    const size_t budget = 200 * 1024;
-    p->stage_i = off_bytes + need_i <= budget;
-    p->stage_u = off_bytes + (p->stage_i ? need_i : 0) + need_u <= budget;
-    p->smem = off_bytes + (p->stage_i ? need_i : 0) + (p->stage_u ? need_u : 0);
+    const size_t n_cells = (size_t)B * B;
 
     auto fail = [&](int rc) { plan_free(p); return rc; };
 #define PLAN_CUDA(expr)                                                                        \
@@ -348,22 +509,27 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         }                                                                                      \
     } while (0)
     const size_t n1 = (size_t)std::max<int64_t>(n, 1);
-    const size_t nkeys = (size_t)B * B * p->W * p->W;
-    PLAN_CUDA(cudaMalloc(&p->ul, n1 * 4));
-    PLAN_CUDA(cudaMalloc(&p->il, n1 * 4));
-    PLAN_CUDA(cudaMalloc(&p->r, n1 * 4));
-    PLAN_CUDA(cudaMalloc(&p->off, (nkeys + 1) * 4));
-    PLAN_CUDA(cudaMalloc(&p->flags, (size_t)B * 4));
-    PLAN_CUDA(cudaMalloc(&p->pu, (size_t)n_users * p->FP * 4));
-    PLAN_CUDA(cudaMalloc(&p->qi, (size_t)n_items * p->FP * 4));
-    PLAN_CUDA(cudaMalloc(&p->bu, (size_t)n_users * 4));
-    PLAN_CUDA(cudaMalloc(&p->bi, (size_t)n_items * 4));
+    PLAN_CUDA(cudaMallocAsync(&p->ul, n1 * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->il, n1 * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->r, n1 * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->off, (n_cells + 1) * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->wave_off, n_cells * (NW + 1) * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->flags, (size_t)B * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->prof, (size_t)B * 8 * 8, st));
+    PLAN_CUDA(cudaMallocAsync(&p->pu, (size_t)n_users * p->FP * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->qi, (size_t)n_items * p->FP * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->bu, (size_t)n_users * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->bi, (size_t)n_items * 4, st));
 
-    // stratify: key -> stable radix sort -> gather records -> offsets
+    // stratify: cell key -> stable radix sort -> per-cell colouring + counting sort -> wave tables
     unsigned *key = nullptr, *key2 = nullptr;
     int *val = nullptr, *val2 = nullptr, *cnt = nullptr, *status = nullptr;
+    uint8_t* color_tmp = nullptr;
     void* tmp = nullptr;
-    auto cleanup = [&]() { cudaFree(key); cudaFree(key2); cudaFree(val); cudaFree(val2); cudaFree(cnt); cudaFree(status); cudaFree(tmp); };
+    auto cleanup = [&]() {
+        free_async(key, st); free_async(key2, st); free_async(val, st); free_async(val2, st); free_async(cnt, st);
+        free_async(status, st); free_async(tmp, st); free_async(color_tmp, st);
+    };
 #define PREP_CUDA(expr)                                                                        \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \
@@ -373,43 +539,71 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
             return fail(SB2_ERR_CUDA);                                                         \
         }                                                                                      \
     } while (0)
-    PREP_CUDA(cudaMalloc(&key, n1 * 4));
-    PREP_CUDA(cudaMalloc(&key2, n1 * 4));
-    PREP_CUDA(cudaMalloc(&val, n1 * 4));
-    PREP_CUDA(cudaMalloc(&val2, n1 * 4));
-    PREP_CUDA(cudaMalloc(&cnt, (nkeys + 1) * 4));
-    PREP_CUDA(cudaMalloc(&status, 4));
-    PREP_CUDA(cudaMemsetAsync(cnt, 0, (nkeys + 1) * 4, st));
-    PREP_CUDA(cudaMemsetAsync(status, 0, 4, st));
+    PREP_CUDA(cudaMallocAsync(&key, n1 * 4, st));
+    PREP_CUDA(cudaMallocAsync(&key2, n1 * 4, st));
+    PREP_CUDA(cudaMallocAsync(&val, n1 * 4, st));
+    PREP_CUDA(cudaMallocAsync(&val2, n1 * 4, st));
+    PREP_CUDA(cudaMallocAsync(&color_tmp, n1, st));
+    PREP_CUDA(cudaMallocAsync(&cnt, (n_cells + 1) * 4, st));
+    PREP_CUDA(cudaMallocAsync(&status, 8, st));
+    PREP_CUDA(cudaMemsetAsync(cnt, 0, (n_cells + 1) * 4, st));
+    PREP_CUDA(cudaMemsetAsync(status, 0, 8, st));
     int end_bit = 1;
-    while (((size_t)1 << end_bit) < nkeys) ++end_bit;
+    while (((size_t)1 << end_bit) < n_cells) ++end_bit;
     size_t tb1 = 0, tb2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, key, key2, val, val2, (int)n, 0, end_bit, st);
-    cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt, p->off, (int)(nkeys + 1), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt, p->off, (int)(n_cells + 1), st);
     const size_t tb = std::max(tb1, tb2);
-    PREP_CUDA(cudaMalloc(&tmp, tb + 16));
+    PREP_CUDA(cudaMallocAsync(&tmp, tb + 16, st));
+    const size_t mask_bytes = (size_t)(max_ul + max_il) * 8;
+    if (mask_bytes > 200 * 1024) {
+        set_error("svd_plan: %d + %d rows per block exceed the colouring kernel's shared memory", max_ul, max_il);
+        cleanup();
+        return fail(SB2_ERR_UNSUPPORTED);
+    }
     if (n > 0) {
         const unsigned nb = (unsigned)ceil_div(n, 256);
-        dsgd_key_kernel<<<nb, 256, 0, st>>>(n, u, i, B, p->W, (int)n_users, (int)n_items, key, val, status);
+        dsgd_key_kernel<<<nb, 256, 0, st>>>(n, u, i, B, (int)n_users, (int)n_items, key, val, cnt, status);
         launch_counter()++;
         size_t t1 = tb;
         PREP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t1, key, key2, val, val2, (int)n, 0, end_bit, st));
         launch_counter()++;
-        dsgd_gather_kernel<<<nb, 256, 0, st>>>(n, val2, key2, u, i, r, B, p->ul, p->il, p->r, cnt);
-        launch_counter()++;
     }
     size_t t2 = tb;
-    PREP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t2, cnt, p->off, (int)(nkeys + 1), st));
+    PREP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t2, cnt, p->off, (int)(n_cells + 1), st));
     launch_counter()++;
-    int status_h = 0;
-    PREP_CUDA(cudaMemcpyAsync(&status_h, status, 4, cudaMemcpyDeviceToHost, st));
+    {
+        PREP_CUDA(cudaFuncSetAttribute(dsgd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
+        const unsigned grid = (unsigned)std::min<size_t>(n_cells, (size_t)sm_count() * 32);
+        dsgd_color_kernel<<<grid, 32, mask_bytes, st>>>((int)n_cells, B, max_ul, max_il, p->off, val2, u, i, r, color_tmp,
+                                                        p->ul, p->il, p->r, p->wave_off, status);
+        launch_counter()++;
+    }
+    int status_h[2] = {0, 0};
+    PREP_CUDA(cudaMemcpyAsync(status_h, status, 8, cudaMemcpyDeviceToHost, st));
     PREP_CUDA(cudaStreamSynchronize(st));
     PREP_CUDA(cudaGetLastError());
     cleanup();
-    if (status_h) {
+    if (status_h[0]) {
         set_error("svd_plan: user / item index out of range");
         return fail(SB2_ERR_INVALID);
     }
+    // shared-memory plan: wave table + cell offsets, item block (moves every stratum), user block, then
+    // as many of a cell's records as still fit (the rest is read from global memory)
+    const size_t budget = 200 * 1024;
+    const size_t fixed = (size_t)(NW + 1 + 2 * B) * 4 + 64;
+    const size_t need_i = (size_t)max_il * (p->FP + 1) * sizeof(float) + 16;
+    const size_t need_u = (size_t)max_ul * (p->FP + 1) * sizeof(float) + 16;
+    const size_t min_rec = 256 * 12;
+    p->stage_i = fixed + min_rec + need_i <= budget;
+    p->stage_u = p->stage_i && fixed + min_rec + need_i + need_u <= budget;
+    size_t used = fixed + (p->stage_i ? need_i : 0) + (p->stage_u ? need_u : 0);
+    int rec_cap = std::max(status_h[1], 1);
+    rec_cap = (int)std::min<size_t>((size_t)rec_cap, (budget - used) / 12);
+    rec_cap = (int)round_up(rec_cap, 4);
+    p->rec_cap = rec_cap;
+    p->max_cell = status_h[1];
+    p->smem = used + (size_t)rec_cap * 12 + 64;
     *out = p;
     return SB2_OK;
 }
@@ -433,19 +627,21 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     a.n_users = (int)p->n_users; a.n_items = (int)p->n_items; a.B = p->B; a.W = p->W;
     a.f = p->prm.n_factors; a.FP = p->FP;
     a.max_ul = (int)ceil_div(p->n_users, p->B); a.max_il = (int)ceil_div(p->n_items, p->B);
-    a.ul = p->ul; a.il = p->il; a.r = p->r; a.off = p->off;
+    a.ul = p->ul; a.il = p->il; a.r = p->r; a.cell_off = p->off; a.wave_off = p->wave_off; a.rec_cap = p->rec_cap;
     a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags;
     const sb2_sgd_params& q = p->prm;
     a.mu = q.biased ? (float)q.global_mean : 0.f;
     a.lr_bu = (float)q.lr_bu; a.lr_bi = (float)q.lr_bi; a.lr_pu = (float)q.lr_pu; a.lr_qi = (float)q.lr_qi;
     a.reg_bu = (float)q.reg_bu; a.reg_bi = (float)q.reg_bi; a.reg_pu = (float)q.reg_pu; a.reg_qi = (float)q.reg_qi;
     a.n_epochs = n_epochs;
+    a.prof = p->prof;
     SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+    if (!p->fast) return dsgd_launch_g<32, false>(p, a, st);
     switch (p->G) {
-        case 4: return dsgd_launch_g<4>(p, a, st);
-        case 8: return dsgd_launch_g<8>(p, a, st);
-        case 16: return dsgd_launch_g<16>(p, a, st);
-        default: return dsgd_launch_g<32>(p, a, st);
+        case 4: return dsgd_launch_g<4, true>(p, a, st);
+        case 8: return dsgd_launch_g<8, true>(p, a, st);
+        case 16: return dsgd_launch_g<16, true>(p, a, st);
+        default: return dsgd_launch_g<32, true>(p, a, st);
     }
 }
 
@@ -475,11 +671,19 @@ void svd_plan_destroy(sb2_svd_plan* p) { plan_free(p); }
 // Use caller-owned fp32 factor buffers (rows x FP, FP = n_factors rounded up to 4): the multi-GPU ring
 // keeps one user block and a rotating item block per rank in torch tensors and binds them per sub-epoch.
 void svd_plan_bind(sb2_svd_plan* p, float* pu, float* qi, float* bu, float* bi) {
-    if (p->owns_factors) { cudaFree(p->pu); cudaFree(p->qi); cudaFree(p->bu); cudaFree(p->bi); }
+    if (p->owns_factors) {
+        free_async(p->pu, p->alloc_stream); free_async(p->qi, p->alloc_stream);
+        free_async(p->bu, p->alloc_stream); free_async(p->bi, p->alloc_stream);
+    }
     p->owns_factors = false;
     p->pu = pu; p->qi = qi; p->bu = bu; p->bi = bi;
 }
 int svd_plan_stride(const sb2_svd_plan* p) { return p->FP; }
+// cycles spent by each CTA of the last run in {flag wait, block load, updates, write-back}: host array [B][8] (see DsgdArgs::prof)
+int svd_plan_profile(const sb2_svd_plan* p, long long* out_host) {
+    SB2_CUDA(cudaMemcpy(out_host, p->prof, (size_t)p->B * 8 * 8, cudaMemcpyDeviceToHost));
+    return SB2_OK;
+}
 // algorithmic bytes per rating update: read + write pu[u], qi[i], bu[u], bi[i] at fp32 + (u, i, r)
 int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p) { return 2ll * (2ll * p->prm.n_factors + 2) * 4 + 12; }
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w) {

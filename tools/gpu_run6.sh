@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/t_all.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_n1.err; cat gpurun_out/bench_n1.json
+timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+echo "bench ncu rc=$?"
+timeout 300 python tools/profile_sim.py > gpurun_out/sim_plain.log 2>&1 && \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_u8_tc -s 1 -c 1 -f -o gpurun_out/gemm_prof python tools/profile_sim.py > gpurun_out/gemm_ncu_full.log 2>&1
+echo "gemm ncu rc=$?"; cat gpurun_out/sim_plain.log

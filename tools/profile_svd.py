@@ -16,7 +16,7 @@ lib = nat.lib()
 plan = C.c_void_p()
 nat.check(lib.sb2_svd_plan_create(ts.n_users, ts.n_items, len(rr), nat.hptr(uu), nat.hptr(ii), nat.hptr(rr), C.byref(prm),
                                   0, C.byref(plan)))
-for it in range(2):
+for it in range(2 if not os.environ.get('QUIET') else 1):
     nat.check(lib.sb2_svd_plan_reset(plan, nat.hptr(pu0), nat.hptr(qi0), None))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -27,4 +27,12 @@ for it in range(2):
 b, w = C.c_int(), C.c_int()
 lib.sb2_svd_plan_grid(plan, C.byref(b), C.byref(w))
 print("grid B=%d W=%d" % (b.value, w.value))
+prof = np.zeros((b.value, 8), dtype=np.int64)
+nat.check(lib.sb2_svd_plan_profile(plan, nat.hptr(prof)))
+tot = prof[:, :4].sum(1)
+m = prof.mean(0)
+print("per-CTA cycles (mean over CTAs) wait %.0f load %.0f update %.0f writeback %.0f  total %.0f; per stratum: %s"
+      % (*m[:4], tot.mean(), np.round(m[:4] / (20 * b.value))))
+print("group0: %.0f cycles per update (%.1f updates/stratum); %.1f waves/stratum; update-phase cycles per wave %.0f"
+      % (m[4] / max(m[5], 1), m[5] / (20 * b.value), m[6] / (20 * b.value), m[2] / max(m[6], 1)))
 lib.sb2_svd_plan_destroy(plan)
