@@ -37,6 +37,8 @@ constexpr int NW = 64;  // waves per cell: 63 colours + 1 sequential tail
 struct DsgdArgs {
     int n_users, n_items, B, W, f, FP;  // FP = n_factors rounded up to 4
     int max_ul, max_il;                 // rows per user / item block (ceil)
+    int US;                             // user row stride: FP (SVD) or 3*FP (SVD++: [p | z | g], see below)
+    int s_begin, s_end;                 // strata of this launch (SVD: all B; SVD++: one chunk)
     int rec_cap;                        // records of a cell staged in shared memory
     const int* ul;                      // records grouped by cell (stratum-major), colour-sorted inside a cell
     const int* il;
@@ -47,8 +49,10 @@ struct DsgdArgs {
     float* qi;                          // n_items x FP
     float* bu;
     float* bi;
+    const float* isq;                   // SVD++: 1/sqrt(|I_u|) per user
+    float* cnt;                         // SVD++: ratings of u processed since the last y_j application
     int* flags;                         // B step counters (ring hand-off of item blocks)
-    float mu, lr_bu, lr_bi, lr_pu, lr_qi, reg_bu, reg_bi, reg_pu, reg_qi;
+    float mu, lr_bu, lr_bi, lr_pu, lr_qi, reg_bu, reg_bi, reg_pu, reg_qi, lr_yj, reg_yj;
     int n_epochs;
     long long* prof;                    // optional: [CTA][8]: cycles in {ring wait, block load, updates, write-back, group-0 updates}, #group-0 updates, #waves, 0
 };
@@ -87,22 +91,36 @@ __device__ __forceinline__ void sc_st(float* p, float v) {
 // one rating update by a group of G lanes (all lanes hold the same ul / il / r).
 // FAST: n_factors <= 4 * G, one 128-bit chunk per lane, the rows stay in registers between the dot
 // product and the update.  Otherwise lanes stride over the chunks and re-read the rows.
-template <int G, bool FAST, bool SU, bool SI, bool BIASED>
-__device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float* qrow, float* bup, float* bip, float r,
-                                           int gl, unsigned gmask, int F4) {
+// PP (SVD++): the user row is [p | z | g]: z = sum_{j in I_u} y_j / sqrt|I_u| as of the last y_j application,
+// advanced by the user's own updates (z += lr_yj (err q - reg_yj z), which is exactly what the reference's
+// per-rating y_j updates do to that sum); g accumulates err * q / sqrt|I_u| for the next y_j application.
+template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
+__device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float* qrow, float* bup, float* bip,
+                                           const float* isqp, float* cntp, float r, int gl, unsigned gmask, int F4) {
+    const int FP = F4 * 4;
     if (FAST) {
         const bool act = gl < F4;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 p = zero4, q = zero4, z = zero4, g = zero4;
         if (act) {
             p = row_ld4<SU>(prow + 4 * gl);
             q = row_ld4<SI>(qrow + 4 * gl);
+            if (PP) {
+                z = row_ld4<SU>(prow + FP + 4 * gl);
+                g = row_ld4<SU>(prow + 2 * FP + 4 * gl);
+            }
         }
-        float b_u = 0.f, b_i = 0.f;
+        float b_u = 0.f, b_i = 0.f, isq = 0.f, cnt = 0.f;
         if (BIASED) {
             b_u = sc_ld<SU>(bup);
             b_i = sc_ld<SI>(bip);
         }
-        float dot = (p.x * q.x + p.y * q.y) + (p.z * q.z + p.w * q.w);
+        if (PP) {
+            isq = sc_ld<SU>(isqp);
+            cnt = sc_ld<SU>(cntp);
+        }
+        const float4 pz = PP ? make_float4(p.x + z.x, p.y + z.y, p.z + z.z, p.w + z.w) : p;
+        float dot = (pz.x * q.x + pz.y * q.y) + (pz.z * q.z + pz.w * q.w);
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
         const float err = BIASED ? r - (a.mu + b_u + b_i + dot) : r - dot;
@@ -112,22 +130,41 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
             pn.y = p.y + a.lr_pu * (err * q.y - a.reg_pu * p.y);
             pn.z = p.z + a.lr_pu * (err * q.z - a.reg_pu * p.z);
             pn.w = p.w + a.lr_pu * (err * q.w - a.reg_pu * p.w);
-            qn.x = q.x + a.lr_qi * (err * p.x - a.reg_qi * q.x);
-            qn.y = q.y + a.lr_qi * (err * p.y - a.reg_qi * q.y);
-            qn.z = q.z + a.lr_qi * (err * p.z - a.reg_qi * q.z);
-            qn.w = q.w + a.lr_qi * (err * p.w - a.reg_qi * q.w);
+            qn.x = q.x + a.lr_qi * (err * pz.x - a.reg_qi * q.x);
+            qn.y = q.y + a.lr_qi * (err * pz.y - a.reg_qi * q.y);
+            qn.z = q.z + a.lr_qi * (err * pz.z - a.reg_qi * q.z);
+            qn.w = q.w + a.lr_qi * (err * pz.w - a.reg_qi * q.w);
             row_st4<SU>(prow + 4 * gl, pn);
             row_st4<SI>(qrow + 4 * gl, qn);
+            if (PP) {
+                const float eg = err * isq;
+                float4 zn, gn;
+                zn.x = z.x + a.lr_yj * (err * q.x - a.reg_yj * z.x);
+                zn.y = z.y + a.lr_yj * (err * q.y - a.reg_yj * z.y);
+                zn.z = z.z + a.lr_yj * (err * q.z - a.reg_yj * z.z);
+                zn.w = z.w + a.lr_yj * (err * q.w - a.reg_yj * z.w);
+                gn.x = g.x + eg * q.x; gn.y = g.y + eg * q.y; gn.z = g.z + eg * q.z; gn.w = g.w + eg * q.w;
+                row_st4<SU>(prow + FP + 4 * gl, zn);
+                row_st4<SU>(prow + 2 * FP + 4 * gl, gn);
+            }
         }
-        if (BIASED && gl == 0) {
-            sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
-            sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
+        if (gl == 0) {
+            if (BIASED) {
+                sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
+                sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
+            }
+            if (PP) sc_st<SU>(cntp, cnt + 1.f);
         }
         return;
     }
     float dot = 0.f;
     for (int c = gl; c < F4; c += G) {
-        const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
+        float4 p = row_ld4<SU>(prow + 4 * c);
+        const float4 q = row_ld4<SI>(qrow + 4 * c);
+        if (PP) {
+            const float4 z = row_ld4<SU>(prow + FP + 4 * c);
+            p.x += z.x; p.y += z.y; p.z += z.z; p.w += z.w;
+        }
         dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
     }
 #pragma unroll
@@ -144,28 +181,48 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
     } else {
         err = r - dot;
     }
+    float eg = 0.f;
+    if (PP) {
+        eg = err * sc_ld<SU>(isqp);
+        const float cnt = sc_ld<SU>(cntp);
+        __syncwarp(gmask);
+        if (gl == 0) sc_st<SU>(cntp, cnt + 1.f);
+    }
 #pragma unroll 1
     for (int c = gl; c < F4; c += G) {
         const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
-        float4 pn, qn;
+        float4 pz = p, pn, qn;
+        if (PP) {
+            const float4 z = row_ld4<SU>(prow + FP + 4 * c), g = row_ld4<SU>(prow + 2 * FP + 4 * c);
+            pz.x += z.x; pz.y += z.y; pz.z += z.z; pz.w += z.w;
+            float4 zn, gn;
+            zn.x = z.x + a.lr_yj * (err * q.x - a.reg_yj * z.x);
+            zn.y = z.y + a.lr_yj * (err * q.y - a.reg_yj * z.y);
+            zn.z = z.z + a.lr_yj * (err * q.z - a.reg_yj * z.z);
+            zn.w = z.w + a.lr_yj * (err * q.w - a.reg_yj * z.w);
+            gn.x = g.x + eg * q.x; gn.y = g.y + eg * q.y; gn.z = g.z + eg * q.z; gn.w = g.w + eg * q.w;
+            row_st4<SU>(prow + FP + 4 * c, zn);
+            row_st4<SU>(prow + 2 * FP + 4 * c, gn);
+        }
         pn.x = p.x + a.lr_pu * (err * q.x - a.reg_pu * p.x);
         pn.y = p.y + a.lr_pu * (err * q.y - a.reg_pu * p.y);
         pn.z = p.z + a.lr_pu * (err * q.z - a.reg_pu * p.z);
         pn.w = p.w + a.lr_pu * (err * q.w - a.reg_pu * p.w);
-        qn.x = q.x + a.lr_qi * (err * p.x - a.reg_qi * q.x);
-        qn.y = q.y + a.lr_qi * (err * p.y - a.reg_qi * q.y);
-        qn.z = q.z + a.lr_qi * (err * p.z - a.reg_qi * q.z);
-        qn.w = q.w + a.lr_qi * (err * p.w - a.reg_qi * q.w);
+        qn.x = q.x + a.lr_qi * (err * pz.x - a.reg_qi * q.x);
+        qn.y = q.y + a.lr_qi * (err * pz.y - a.reg_qi * q.y);
+        qn.z = q.z + a.lr_qi * (err * pz.z - a.reg_qi * q.z);
+        qn.w = q.w + a.lr_qi * (err * pz.w - a.reg_qi * q.w);
         row_st4<SU>(prow + 4 * c, pn);
         row_st4<SI>(qrow + 4 * c, qn);
     }
 }
 
 // G lanes per rating, SU / SI: user / item block staged in shared memory, BIASED: SVD(biased=True)
-template <int G, bool FAST, bool SU, bool SI, bool BIASED>
+template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
 __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int B = a.B, W = a.W, FP = a.FP, F4 = a.FP >> 2;
+    const int US = a.US, U4 = a.US >> 2;  // user rows: US floats ([p] or [p | z | g])
     const int ub = blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int gid = tid / G, gl = tid % G;
@@ -174,10 +231,12 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
 
     // shared memory carve-up
     float* pu_s = smem_f;
-    float* qi_s = pu_s + (SU ? (size_t)a.max_ul * FP : 0);
+    float* qi_s = pu_s + (SU ? (size_t)a.max_ul * US : 0);
     float* bu_s = qi_s + (SI ? (size_t)a.max_il * FP : 0);
     float* bi_s = bu_s + (SU ? a.max_ul : 0);
-    int* wave_s = reinterpret_cast<int*>(bi_s + (SI ? a.max_il : 0));
+    float* isq_s = bi_s + (SI ? a.max_il : 0);
+    float* cnt_s = isq_s + ((SU && PP) ? a.max_ul : 0);
+    int* wave_s = reinterpret_cast<int*>(cnt_s + ((SU && PP) ? a.max_ul : 0));
     int* coff_s = wave_s + (NW + 1);          // [2 * B]: cell begin / end per stratum
     int* rul_s = coff_s + 2 * B;
     int* ril_s = rul_s + a.rec_cap;
@@ -185,13 +244,19 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
 
     const int nu_local = (a.n_users - ub + B - 1) / B;
     if (SU) {
-        for (int l = tid / F4, c = tid % F4; l < nu_local; ) {
-            reinterpret_cast<float4*>(pu_s)[l * F4 + c] =
-                __ldcg(reinterpret_cast<const float4*>(a.pu + ((size_t)(ub + (size_t)l * B)) * FP) + c);
-            c += nthr % F4; l += nthr / F4;
-            if (c >= F4) { c -= F4; ++l; }
+        for (int l = tid / U4, c = tid % U4; l < nu_local; ) {
+            reinterpret_cast<float4*>(pu_s)[l * U4 + c] =
+                __ldcg(reinterpret_cast<const float4*>(a.pu + ((size_t)(ub + (size_t)l * B)) * US) + c);
+            c += nthr % U4; l += nthr / U4;
+            if (c >= U4) { c -= U4; ++l; }
         }
-        for (int l = tid; l < nu_local; l += nthr) bu_s[l] = __ldcg(a.bu + ub + (size_t)l * B);
+        for (int l = tid; l < nu_local; l += nthr) {
+            bu_s[l] = __ldcg(a.bu + ub + (size_t)l * B);
+            if (PP) {
+                isq_s[l] = __ldcg(a.isq + ub + (size_t)l * B);
+                cnt_s[l] = __ldcg(a.cnt + ub + (size_t)l * B);
+            }
+        }
     }
     for (int s = tid; s < B; s += nthr) {
         coff_s[2 * s] = a.cell_off[(size_t)s * B + ub];
@@ -200,10 +265,11 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
     __syncthreads();
 
     long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, t_proc = 0, n_proc = 0, n_wave = 0;
+    const int n_strata = a.s_end - a.s_begin;
     for (int ep = 0; ep < a.n_epochs; ++ep) {
-        for (int s = 0; s < B; ++s) {
+        for (int s = a.s_begin; s < a.s_end; ++s) {
             const int ib = (ub + s) % B;
-            const int step = ep * B + s;
+            const int step = ep * n_strata + (s - a.s_begin);
             const long long c0 = clock64();
             // this stratum's records and wave table do not depend on the ring: fetch them while waiting
             const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
@@ -249,11 +315,13 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
                 float r;
                 if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
                 else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
-                float* prow = SU ? pu_s + (size_t)ul * FP : a.pu + ((size_t)(ub + (size_t)ul * B)) * FP;
+                float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
                 float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
                 float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
                 float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
-                sgd_update<G, FAST, SU, SI, BIASED>(a, prow, qrow, bup, bip, r, gl, gmask, F4);
+                const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
+                float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
+                sgd_update<G, FAST, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, gmask, F4);
             };
             for (int w = 0; w < NW - 1; ++w) {
                 const int wb = wave_s[w], we = wave_s[w + 1];
@@ -300,14 +368,16 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
         a.prof[ub * 8 + 4] = t_proc; a.prof[ub * 8 + 5] = n_proc; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = 0;
     }
     if (SU) {
-        for (int l = tid / F4, c = tid % F4; l < nu_local; ) {
-            __stcg(reinterpret_cast<float4*>(a.pu + ((size_t)(ub + (size_t)l * B)) * FP) + c,
-                   reinterpret_cast<const float4*>(pu_s)[l * F4 + c]);
-            c += nthr % F4; l += nthr / F4;
-            if (c >= F4) { c -= F4; ++l; }
+        for (int l = tid / U4, c = tid % U4; l < nu_local; ) {
+            __stcg(reinterpret_cast<float4*>(a.pu + ((size_t)(ub + (size_t)l * B)) * US) + c,
+                   reinterpret_cast<const float4*>(pu_s)[l * U4 + c]);
+            c += nthr % U4; l += nthr / U4;
+            if (c >= U4) { c -= U4; ++l; }
         }
-        if (BIASED)
-            for (int l = tid; l < nu_local; l += nthr) __stcg(a.bu + ub + (size_t)l * B, bu_s[l]);
+        for (int l = tid; l < nu_local; l += nthr) {
+            if (BIASED) __stcg(a.bu + ub + (size_t)l * B, bu_s[l]);
+            if (PP) __stcg(a.cnt + ub + (size_t)l * B, cnt_s[l]);
+        }
     }
 }
 
@@ -381,19 +451,89 @@ __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int 
     }
 }
 
-__global__ void f64_to_rows_kernel(int64_t rows, int f, int FP, const double* __restrict__ src, float* __restrict__ dst) {
+// fp64 (rows x f) -> fp32 rows of `stride` floats: [0, f) = src, [f, stride) = 0
+__global__ void f64_to_rows_kernel(int64_t rows, int f, int stride, const double* __restrict__ src, float* __restrict__ dst) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= rows * FP) return;
-    const int64_t row = t / FP;
-    const int c = (int)(t % FP);
+    if (t >= rows * stride) return;
+    const int64_t row = t / stride;
+    const int c = (int)(t % stride);
     dst[t] = c < f ? (float)src[row * f + c] : 0.f;
 }
-__global__ void rows_to_f64_kernel(int64_t rows, int f, int FP, const float* __restrict__ src, double* __restrict__ dst) {
+
+// ---- SVD++ companions of the stratified kernel --------------------------------------------------
+// z_u = sum_{j in I_u} y_j / sqrt|I_u|  (matrix_factorization.pyx:472-476), and reset of g_u / cnt_u.
+// One warp per user; user rows are [p | z | g] with stride US = 3 * FP.
+__global__ void svdpp_user_refresh_kernel(int64_t n_users, int FP, const int64_t* __restrict__ u_ptr,
+                                          const int32_t* __restrict__ ui_idx, const float* __restrict__ yj,
+                                          const float* __restrict__ isq, float* __restrict__ urows,
+                                          float* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_users) return;
+    const int64_t b = u_ptr[u], e = u_ptr[u + 1];
+    const float w = isq[u];
+    float* row = urows + (size_t)u * 3 * FP;
+    for (int c = lane; c < FP; c += 32) {
+        float acc = 0.f;
+        for (int64_t a = b; a < e; ++a) acc += yj[(size_t)ui_idx[a] * FP + c];
+        row[FP + c] = acc * w;
+        row[2 * FP + c] = 0.f;
+    }
+    if (lane == 0) cnt[u] = 0.f;
+}
+
+// y_j <- y_j (1 - lr reg)^{c_j} + lr sum_{u in U_j} g_u,  c_j = sum_{u in U_j} cnt_u: what the reference's
+// per-rating updates y_j += lr (err q / sqrt|I_u| - reg y_j) (matrix_factorization.pyx:496-498) add up
+// to over the ratings processed since the last application, with the decay applied exactly.
+__global__ void svdpp_item_apply_kernel(int64_t n_items, int FP, const int64_t* __restrict__ i_ptr,
+                                        const int32_t* __restrict__ iu_idx, const float* __restrict__ urows,
+                                        const float* __restrict__ cnt, float lr, float reg, float* __restrict__ yj) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_items) return;
+    const int64_t b = i_ptr[j], e = i_ptr[j + 1];
+    float c = 0.f;
+    for (int64_t a = b + lane; a < e; a += 32) c += cnt[iu_idx[a]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if (c == 0.f) return;
+    const float decay = expf(c * log1pf(-lr * reg));
+    for (int col = lane; col < FP; col += 32) {
+        float acc = 0.f;
+        for (int64_t a = b; a < e; ++a) acc += urows[(size_t)iu_idx[a] * 3 * FP + 2 * FP + col];
+        yj[(size_t)j * FP + col] = yj[(size_t)j * FP + col] * decay + lr * acc;
+    }
+}
+
+__global__ void svdpp_isq_kernel(int64_t n_users, const int64_t* __restrict__ u_ptr, float* __restrict__ isq) {
+    const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u < n_users) {
+        const double n = (double)(u_ptr[u + 1] - u_ptr[u]);
+        isq[u] = n > 0 ? (float)(1.0 / sqrt(n)) : 0.f;
+    }
+}
+__global__ void svdpp_item_count_kernel(int64_t n, const int32_t* __restrict__ i, unsigned long long* cnt, int* max_cnt) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) {
+        const unsigned long long c = atomicAdd(&cnt[i[k]], 1ull) + 1;
+        atomicMax(max_cnt, (int)c);
+    }
+}
+__global__ void svdpp_iota_kernel(int64_t n, int* v) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) v[k] = (int)k;
+}
+__global__ void svdpp_gather_users_kernel(int64_t n, const int* __restrict__ perm, const int32_t* __restrict__ u,
+                                          int32_t* __restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = u[perm[k]];
+}
+__global__ void rows_to_f64_kernel(int64_t rows, int f, int stride, const float* __restrict__ src, double* __restrict__ dst) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= rows * f) return;
     const int64_t row = t / f;
     const int c = (int)(t % f);
-    dst[t] = (double)src[row * FP + c];
+    dst[t] = (double)src[row * stride + c];
 }
 __global__ void f32_to_f64_kernel(int64_t n, const float* __restrict__ src, double* __restrict__ dst) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -415,15 +555,21 @@ struct sb2_svd_plan {
     int rec_cap = 0, max_cell = 0;
     float *r = nullptr, *pu = nullptr, *qi = nullptr, *bu = nullptr, *bi = nullptr;
     bool owns_factors = true;
+    // SVD++ state
+    bool with_yj = false;
+    int US = 0, chunks = 1;
+    float *yj = nullptr, *isq = nullptr, *cnt = nullptr;
+    int64_t *u_ptr = nullptr, *i_ptr = nullptr;
+    int32_t *ui_idx = nullptr, *iu_idx = nullptr;
     cudaStream_t alloc_stream = nullptr;
     long long* prof = nullptr;
 };
 
 namespace sb2 {
 
-template <int G, bool FAST, bool SU, bool SI, bool BIASED>
+template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
 static int dsgd_launch_t(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
-    auto kern = dsgd_svd_kernel<G, FAST, SU, SI, BIASED>;
+    auto kern = dsgd_svd_kernel<G, FAST, SU, SI, BIASED, PP>;
     SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     void* args[] = {(void*)&a};
     SB2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(p->B), dim3(p->W * G), args, p->smem, st));
@@ -433,13 +579,31 @@ static int dsgd_launch_t(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t 
 
 template <int G, bool FAST>
 static int dsgd_launch_g(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
+    // staging plans: both blocks in shared memory, item block only, or neither.  SVD++ is always biased.
+    if (p->with_yj) {
+        if (p->stage_u && p->stage_i) return dsgd_launch_t<G, FAST, true, true, true, true>(p, a, st);
+        if (p->stage_i) return dsgd_launch_t<G, FAST, false, true, true, true>(p, a, st);
+        return dsgd_launch_t<G, FAST, false, false, true, true>(p, a, st);
+    }
     const bool b = p->prm.biased != 0;
-    // staging plans: both blocks in shared memory, item block only, or neither
     if (p->stage_u && p->stage_i)
-        return b ? dsgd_launch_t<G, FAST, true, true, true>(p, a, st) : dsgd_launch_t<G, FAST, true, true, false>(p, a, st);
+        return b ? dsgd_launch_t<G, FAST, true, true, true, false>(p, a, st)
+                 : dsgd_launch_t<G, FAST, true, true, false, false>(p, a, st);
     if (p->stage_i)
-        return b ? dsgd_launch_t<G, FAST, false, true, true>(p, a, st) : dsgd_launch_t<G, FAST, false, true, false>(p, a, st);
-    return b ? dsgd_launch_t<G, FAST, false, false, true>(p, a, st) : dsgd_launch_t<G, FAST, false, false, false>(p, a, st);
+        return b ? dsgd_launch_t<G, FAST, false, true, true, false>(p, a, st)
+                 : dsgd_launch_t<G, FAST, false, true, false, false>(p, a, st);
+    return b ? dsgd_launch_t<G, FAST, false, false, true, false>(p, a, st)
+             : dsgd_launch_t<G, FAST, false, false, false, false>(p, a, st);
+}
+
+static int dsgd_launch(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
+    if (!p->fast) return dsgd_launch_g<32, false>(p, a, st);
+    switch (p->G) {
+        case 4: return dsgd_launch_g<4, true>(p, a, st);
+        case 8: return dsgd_launch_g<8, true>(p, a, st);
+        case 16: return dsgd_launch_g<16, true>(p, a, st);
+        default: return dsgd_launch_g<32, true>(p, a, st);
+    }
 }
 
 static void free_async(void* q, cudaStream_t st) {
@@ -451,6 +615,8 @@ static void plan_free(sb2_svd_plan* p) {
     cudaStream_t st = p->alloc_stream;
     free_async(p->ul, st); free_async(p->il, st); free_async(p->off, st); free_async(p->wave_off, st); free_async(p->flags, st);
     free_async(p->r, st); free_async(p->prof, st);
+    free_async(p->yj, st); free_async(p->isq, st); free_async(p->cnt, st); free_async(p->u_ptr, st);
+    free_async(p->i_ptr, st); free_async(p->ui_idx, st); free_async(p->iu_idx, st);
     if (p->owns_factors) { free_async(p->pu, st); free_async(p->qi, st); free_async(p->bu, st); free_async(p->bi, st); }
     delete p;
 }
@@ -459,9 +625,9 @@ static void plan_free(sb2_svd_plan* p) {
 int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
                         const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
                         const int32_t* ui_idx, cudaStream_t st, sb2_svd_plan** out) {
-    if (with_yj) {
-        set_error("svdpp: not implemented in this build");
-        return SB2_ERR_UNSUPPORTED;
+    if (with_yj && (!u_ptr || !ui_idx)) {
+        set_error("svdpp plan: the ur CSR (u_ptr, ui_idx) is required");
+        return SB2_ERR_INVALID;
     }
     if (n_users <= 0 || n_items <= 0 || n < 0 || n > 0x7FFFFFF0ll || prm->n_factors <= 0 || prm->n_factors > 1024) {
         set_error("svd_plan: invalid shape");
@@ -470,8 +636,10 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     sb2_svd_plan* p = new sb2_svd_plan();
     p->n_users = n_users; p->n_items = n_items; p->n = n; p->prm = *prm;
     p->alloc_stream = st;
+    p->with_yj = with_yj != 0;
     const int f = prm->n_factors;
     p->FP = (int)round_up(f, 4);
+    p->US = p->with_yj ? 3 * p->FP : p->FP;
     const int F4 = p->FP / 4;
     // lanes per rating: the smallest power of two covering the row in 128-bit chunks (one chunk per lane,
     // rows stay in registers); rows longer than 128 factors fall back to 32 lanes striding the row.
@@ -516,7 +684,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     PLAN_CUDA(cudaMallocAsync(&p->wave_off, n_cells * (NW + 1) * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->flags, (size_t)B * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->prof, (size_t)B * 8 * 8, st));
-    PLAN_CUDA(cudaMallocAsync(&p->pu, (size_t)n_users * p->FP * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->pu, (size_t)n_users * p->US * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->qi, (size_t)n_items * p->FP * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->bu, (size_t)n_users * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->bi, (size_t)n_items * 4, st));
@@ -588,12 +756,78 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         set_error("svd_plan: user / item index out of range");
         return fail(SB2_ERR_INVALID);
     }
+    if (p->with_yj) {
+        // ur CSR copy, 1/sqrt|I_u|, ir CSR (item -> raters) for the y_j application, chunk count
+        PLAN_CUDA(cudaMallocAsync(&p->yj, (size_t)n_items * p->FP * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->isq, (size_t)n_users * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->cnt, (size_t)n_users * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->u_ptr, (size_t)(n_users + 1) * 8, st));
+        PLAN_CUDA(cudaMallocAsync(&p->i_ptr, (size_t)(n_items + 1) * 8, st));
+        PLAN_CUDA(cudaMallocAsync(&p->ui_idx, n1 * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->iu_idx, n1 * 4, st));
+        PLAN_CUDA(cudaMemcpyAsync(p->u_ptr, u_ptr, (size_t)(n_users + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        PLAN_CUDA(cudaMemcpyAsync(p->ui_idx, ui_idx, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        PLAN_CUDA(cudaMemsetAsync(p->cnt, 0, (size_t)n_users * 4, st));
+        svdpp_isq_kernel<<<(unsigned)ceil_div(n_users, 256), 256, 0, st>>>(n_users, p->u_ptr, p->isq);
+        launch_counter()++;
+        unsigned long long* icnt = nullptr;
+        int *maxc = nullptr, *perm_in = nullptr, *perm_out = nullptr, *keys_out = nullptr;
+        void* tmp2 = nullptr;
+        auto cleanup2 = [&]() {
+            free_async(icnt, st); free_async(maxc, st); free_async(perm_in, st); free_async(perm_out, st);
+            free_async(keys_out, st); free_async(tmp2, st);
+        };
+#define PP_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            cleanup2();                                                                        \
+            return fail(SB2_ERR_CUDA);                                                         \
+        }                                                                                      \
+    } while (0)
+        PP_CUDA(cudaMallocAsync(&icnt, (size_t)(n_items + 1) * 8, st));
+        PP_CUDA(cudaMallocAsync(&maxc, 4, st));
+        PP_CUDA(cudaMallocAsync(&perm_in, n1 * 4, st));
+        PP_CUDA(cudaMallocAsync(&perm_out, n1 * 4, st));
+        PP_CUDA(cudaMallocAsync(&keys_out, n1 * 4, st));
+        PP_CUDA(cudaMemsetAsync(icnt, 0, (size_t)(n_items + 1) * 8, st));
+        PP_CUDA(cudaMemsetAsync(maxc, 0, 4, st));
+        size_t s1 = 0, s2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, s1, reinterpret_cast<int64_t*>(icnt), p->i_ptr, (int)(n_items + 1), st);
+        cub::DeviceRadixSort::SortPairs(nullptr, s2, i, keys_out, perm_in, perm_out, (int)n, 0, 32, st);
+        const size_t sb = std::max(s1, s2);
+        PP_CUDA(cudaMallocAsync(&tmp2, sb + 16, st));
+        if (n > 0) {
+            const unsigned nb = (unsigned)ceil_div(n, 256);
+            svdpp_item_count_kernel<<<nb, 256, 0, st>>>(n, i, icnt, maxc);
+            svdpp_iota_kernel<<<nb, 256, 0, st>>>(n, perm_in);
+            size_t t3 = sb;
+            PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp2, t3, i, keys_out, perm_in, perm_out, (int)n, 0, 32, st));
+            svdpp_gather_users_kernel<<<nb, 256, 0, st>>>(n, perm_out, u, p->iu_idx);
+            launch_counter() += 4;
+        }
+        size_t t4 = sb;
+        PP_CUDA(cub::DeviceScan::ExclusiveSum(tmp2, t4, reinterpret_cast<int64_t*>(icnt), p->i_ptr, (int)(n_items + 1), st));
+        launch_counter()++;
+        int max_raters = 0;
+        PP_CUDA(cudaMemcpyAsync(&max_raters, maxc, 4, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+        cleanup2();
+        // y_j is applied `chunks` times per epoch: a popular item must not receive more than ~32 raters'
+        // accumulated gradients in one step (tools/proto/svdpp_variants.py, DESIGN.md "SVD++")
+        p->chunks = std::max(1, std::min(B, (int)ceil_div(max_raters, 32)));
+        if (const char* e = getenv("SB2_SVDPP_CHUNKS")) {
+            const int c = atoi(e);
+            if (c >= 1) p->chunks = std::min(c, B);
+        }
+    }
     // shared-memory plan: wave table + cell offsets, item block (moves every stratum), user block, then
     // as many of a cell's records as still fit (the rest is read from global memory)
     const size_t budget = 200 * 1024;
     const size_t fixed = (size_t)(NW + 1 + 2 * B) * 4 + 64;
     const size_t need_i = (size_t)max_il * (p->FP + 1) * sizeof(float) + 16;
-    const size_t need_u = (size_t)max_ul * (p->FP + 1) * sizeof(float) + 16;
+    const size_t need_u = (size_t)max_ul * (p->US + 3) * sizeof(float) + 16;
     const size_t min_rec = 256 * 12;
     p->stage_i = fixed + min_rec + need_i <= budget;
     p->stage_u = p->stage_i && fixed + min_rec + need_i + need_u <= budget;
@@ -611,10 +845,19 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
 // pu0 / qi0: DEVICE fp64 (n_users x f), (n_items x f)
 int svd_plan_reset_dev(sb2_svd_plan* p, const double* pu0, const double* qi0, const double* yj0, cudaStream_t st) {
     const int f = p->prm.n_factors;
-    f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_users * p->FP, 256), 256, 0, st>>>(p->n_users, f, p->FP, pu0, p->pu);
+    f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_users * p->US, 256), 256, 0, st>>>(p->n_users, f, p->US, pu0, p->pu);
     SB2_LAUNCH_CHECK();
     f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, f, p->FP, qi0, p->qi);
     SB2_LAUNCH_CHECK();
+    if (p->with_yj) {
+        if (!yj0) {
+            set_error("svd_plan_reset: yj required for SVD++");
+            return SB2_ERR_INVALID;
+        }
+        f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, f, p->FP, yj0, p->yj);
+        SB2_LAUNCH_CHECK();
+        SB2_CUDA(cudaMemsetAsync(p->cnt, 0, (size_t)p->n_users * 4, st));
+    }
     SB2_CUDA(cudaMemsetAsync(p->bu, 0, (size_t)p->n_users * 4, st));
     SB2_CUDA(cudaMemsetAsync(p->bi, 0, (size_t)p->n_items * 4, st));
     return SB2_OK;
@@ -625,35 +868,55 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     DsgdArgs a;
     memset(&a, 0, sizeof(a));
     a.n_users = (int)p->n_users; a.n_items = (int)p->n_items; a.B = p->B; a.W = p->W;
-    a.f = p->prm.n_factors; a.FP = p->FP;
+    a.f = p->prm.n_factors; a.FP = p->FP; a.US = p->US;
     a.max_ul = (int)ceil_div(p->n_users, p->B); a.max_il = (int)ceil_div(p->n_items, p->B);
     a.ul = p->ul; a.il = p->il; a.r = p->r; a.cell_off = p->off; a.wave_off = p->wave_off; a.rec_cap = p->rec_cap;
     a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags;
+    a.isq = p->isq; a.cnt = p->cnt;
     const sb2_sgd_params& q = p->prm;
-    a.mu = q.biased ? (float)q.global_mean : 0.f;
+    a.mu = (q.biased || p->with_yj) ? (float)q.global_mean : 0.f;
     a.lr_bu = (float)q.lr_bu; a.lr_bi = (float)q.lr_bi; a.lr_pu = (float)q.lr_pu; a.lr_qi = (float)q.lr_qi;
     a.reg_bu = (float)q.reg_bu; a.reg_bi = (float)q.reg_bi; a.reg_pu = (float)q.reg_pu; a.reg_qi = (float)q.reg_qi;
-    a.n_epochs = n_epochs;
+    a.lr_yj = (float)q.lr_yj; a.reg_yj = (float)q.reg_yj;
     a.prof = p->prof;
-    SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
-    if (!p->fast) return dsgd_launch_g<32, false>(p, a, st);
-    switch (p->G) {
-        case 4: return dsgd_launch_g<4, true>(p, a, st);
-        case 8: return dsgd_launch_g<8, true>(p, a, st);
-        case 16: return dsgd_launch_g<16, true>(p, a, st);
-        default: return dsgd_launch_g<32, true>(p, a, st);
+    if (!p->with_yj) {
+        a.n_epochs = n_epochs; a.s_begin = 0; a.s_end = p->B;
+        SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+        return dsgd_launch(p, a, st);
     }
+    // SVD++: per epoch `chunks` x { refresh z_u and clear g_u; strata of the chunk; apply g to y_j }
+    const unsigned ub = (unsigned)ceil_div(p->n_users * 32, 256), ib = (unsigned)ceil_div(p->n_items * 32, 256);
+    for (int ep = 0; ep < n_epochs; ++ep)
+        for (int c = 0; c < p->chunks; ++c) {
+            a.n_epochs = 1;
+            a.s_begin = (int)((int64_t)p->B * c / p->chunks);
+            a.s_end = (int)((int64_t)p->B * (c + 1) / p->chunks);
+            if (a.s_begin == a.s_end) continue;
+            svdpp_user_refresh_kernel<<<ub, 256, 0, st>>>(p->n_users, p->FP, p->u_ptr, p->ui_idx, p->yj, p->isq, p->pu,
+                                                          p->cnt);
+            SB2_LAUNCH_CHECK();
+            SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+            SB2_TRY(dsgd_launch(p, a, st));
+            svdpp_item_apply_kernel<<<ib, 256, 0, st>>>(p->n_items, p->FP, p->i_ptr, p->iu_idx, p->pu, p->cnt, a.lr_yj,
+                                                        a.reg_yj, p->yj);
+            SB2_LAUNCH_CHECK();
+        }
+    return SB2_OK;
 }
 
 // outputs: DEVICE fp64
 int svd_plan_read_dev(sb2_svd_plan* p, double* pu, double* qi, double* bu, double* bi, double* yj, cudaStream_t st) {
     const int f = p->prm.n_factors;
     if (pu) {
-        rows_to_f64_kernel<<<(unsigned)ceil_div(p->n_users * f, 256), 256, 0, st>>>(p->n_users, f, p->FP, p->pu, pu);
+        rows_to_f64_kernel<<<(unsigned)ceil_div(p->n_users * f, 256), 256, 0, st>>>(p->n_users, f, p->US, p->pu, pu);
         SB2_LAUNCH_CHECK();
     }
     if (qi) {
         rows_to_f64_kernel<<<(unsigned)ceil_div(p->n_items * f, 256), 256, 0, st>>>(p->n_items, f, p->FP, p->qi, qi);
+        SB2_LAUNCH_CHECK();
+    }
+    if (yj && p->with_yj) {
+        rows_to_f64_kernel<<<(unsigned)ceil_div(p->n_items * f, 256), 256, 0, st>>>(p->n_items, f, p->FP, p->yj, yj);
         SB2_LAUNCH_CHECK();
     }
     if (bu) {
@@ -685,13 +948,19 @@ int svd_plan_profile(const sb2_svd_plan* p, long long* out_host) {
     return SB2_OK;
 }
 // algorithmic bytes per rating update: read + write pu[u], qi[i], bu[u], bi[i] at fp32 + (u, i, r)
-int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p) { return 2ll * (2ll * p->prm.n_factors + 2) * 4 + 12; }
+int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p) {
+    const long long f = p->prm.n_factors;
+    // SVD++ (per-user batched y_j): + read/write of z_u and g_u with every rating, + one y_j row read (refresh)
+    // and one g_u row read (application) per rating and chunk
+    if (p->with_yj) return 2ll * (4 * f + 2) * 4 + 12 + 2ll * p->chunks * f * 4;
+    return 2ll * (2 * f + 2) * 4 + 12;
+}
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w) {
     if (b) *b = p->B;
     if (w) *w = p->W;
 }
 void svd_plan_dims(const sb2_svd_plan* p, int64_t* n_users, int64_t* n_items, int* f, int* with_yj) {
-    *n_users = p->n_users; *n_items = p->n_items; *f = p->prm.n_factors; *with_yj = 0;
+    *n_users = p->n_users; *n_items = p->n_items; *f = p->prm.n_factors; *with_yj = p->with_yj ? 1 : 0;
 }
 
 }  // namespace sb2

@@ -413,6 +413,46 @@ def test_svd_conflict_free_input_matches_oracle():
         assert np.allclose(algo.bu, bu, rtol=0, atol=2e-6) and np.allclose(algo.bi, bi, rtol=0, atol=2e-6)
 
 
+def test_u1_svdpp_rmse(u1, u1_golden):
+    ts, testset = u1
+    algo = sb.SVDpp(random_state=0).fit(ts)
+    assert algo.yj.shape == (ts.n_items, 20) and algo.yj.dtype == np.float64
+    preds = algo.test(testset)
+    g = u1_golden["algos"]["SVDpp_rs0"]
+    assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(g["rmse"])) <= RMSE_TOL
+    assert abs(float(sb.accuracy.mae(preds, verbose=False)) - float(g["mae"])) <= RMSE_TOL
+    # estimate() path of SVD++ (implicit term recomputed from yj) against the oracle on the fitted factors
+    iu, ii = inner_pairs(ts, testset)
+    ptr, idx, _ = ts.user_csr()
+    want, _ = oracle.mf_estimate(iu, ii, True, float(ts.global_mean), algo.pu, algo.qi, algo.bu, algo.bi, algo.yj, ptr, idx)
+    got, _ = algo._estimate_batch(iu, ii)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(600, 400, 30_000, 10), (3000, 300, 200_000, 10)])
+def test_synthetic_svdpp_rmse_vs_oracle(shape):
+    """Second shape: every item has ~670 raters -- the regime where applying y_j once per epoch overshoots
+    (tools/proto/svdpp_variants.py); the chunked application must stay within 0.005 of the per-rating reference."""
+    nu, ni, n, epochs = shape
+    d = synth.ratings(nu, ni, n, seed=5)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    uu, ii, rr = ts.coo()
+    ptr, idx, _ = ts.user_csr()
+    tu, ti, tr_ = d["test"]
+    mu = float(ts.global_mean)
+    algo = sb.SVDpp(n_epochs=epochs, random_state=0).fit(ts)
+    rng = np.random.RandomState(0)
+    f = 20
+    pu0 = rng.normal(0, .1, (ts.n_users, f)); qi0 = rng.normal(0, .1, (ts.n_items, f)); yj0 = rng.normal(0, .1, (ts.n_items, f))
+    pu, qi, yj, bu, bi = oracle.svdpp_sgd(uu, ii, rr, ptr, idx, pu0, qi0, yj0, epochs, mu, *([.007] * 5), *([.02] * 5))
+    want, _ = oracle.mf_estimate(tu, ti, True, mu, pu, qi, bu, bi, yj, ptr, idx)
+    got, _ = oracle.mf_estimate(tu, ti, True, mu, algo.pu, algo.qi, algo.bu, algo.bi, algo.yj, ptr, idx)
+    rm = lambda e: float(np.sqrt(np.mean((np.clip(e, 1, 5) - tr_) ** 2)))
+    ma = lambda e: float(np.mean(np.abs(np.clip(e, 1, 5) - tr_)))
+    assert abs(rm(want) - rm(got)) <= RMSE_TOL and abs(ma(want) - ma(got)) <= RMSE_TOL, (rm(want), rm(got))
+
+
 def test_mf_predict_against_oracle(u1):
     ts, testset = u1
     iu, ii = inner_pairs(ts, testset)
@@ -436,7 +476,7 @@ def test_unknown_user_or_item_and_pickle(tmp_path):
     reader = sb.Reader(line_format="user item rating", sep=" ", skip_lines=3, rating_scale=(1, 5))
     data = sb.Dataset.load_from_file(os.path.join(GOLDEN, "custom_dataset"), reader)
     ts = data.build_full_trainset()
-    for klass in (sb.SVD, sb.NMF, sb.KNNBasic, sb.KNNBaseline, sb.BaselineOnly):
+    for klass in (sb.SVD, sb.SVDpp, sb.NMF, sb.KNNBasic, sb.KNNBaseline, sb.BaselineOnly):
         algo = klass()
         algo.fit(ts)
         algo.predict("user0", "unknown_item", None)
