@@ -100,29 +100,16 @@ int baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t*
 // from the OLD pu / qi (the accumulators were built before either update).
 //
 // Each accumulator element is an ordered sum over one user's (one item's) ratings in all_ratings()
-// order.  A group of G = 2^ceil(log2 f) (<= 32) lanes owns one segment; lane l owns factors
-// l, l+G, ...  The dot product for est_k is recomputed inside both passes by chaining the per-factor
-// products in factor order through warp shuffles, so every lane obtains the bit-identical est_k and no
-// N-sized est array ever travels through HBM (unbiased model).  The biased model makes bu/bi a
-// sequential recursion over all ratings (:707-709); that part runs on one thread and hands est_k to
-// the two passes through an array.
+// order.  est_k is computed once per epoch by one thread per rating (factor-ordered mul/add chain, so it
+// carries the reference's bits), stored in all_ratings() order for the user pass and gathered into item
+// order for the item pass; a group of G = 2^ceil(log2 f) (<= 32) lanes then owns one segment, lane l owns
+// factors l, l+G, ...  The biased model makes bu/bi a sequential recursion over all ratings (:707-709); that
+// part runs on one thread between the dot kernel and the passes.
 // =================================================================================================
-template <int G>
-__device__ __forceinline__ double ordered_dot(const double* __restrict__ prow, const double* __restrict__ qrow, int f,
-                                              int gl, unsigned gmask, int gbase) {
-    // all lanes of the group return sum_{j<f} q[j]*p[j] accumulated in index order
-    double dot = 0.0;
-    for (int j0 = 0; j0 < f; j0 += G) {
-        const int j = j0 + gl;
-        const double prod = (j < f) ? __dmul_rn(qrow[j], prow[j]) : 0.0;
-        const int lim = min(G, f - j0);
-        for (int l = 0; l < lim; ++l) dot = __dadd_rn(dot, __shfl_sync(gmask, prod, gbase + l));
-    }
-    return dot;
-}
-
-// One pass: segments are users (side = 0: fixed row = pu[u], gathered rows = qi[i_a]) or items (side = 1).
-// seg_ptr/other_idx/r_seg: CSR of the side in all_ratings() order; est_seg: optional est per entry.
+// One pass: segments are users (fixed row = pu[u], gathered rows = qi[i_a]) or items (the transpose).
+// seg_ptr / other_idx / r_seg / est_seg: CSR of the side in all_ratings() order.  A group of G lanes owns one
+// segment, lane l owns factors l, l+G, ...; the entry loop is unrolled so that the gathers of the next
+// entries are in flight while the two ordered fp64 accumulation chains (num, den) advance.
 template <int G>
 __global__ void nmf_pass_kernel(int64_t n_seg, int f, const int64_t* __restrict__ seg_ptr,
                                 const int32_t* __restrict__ other_idx, const double* __restrict__ r_seg,
@@ -131,29 +118,54 @@ __global__ void nmf_pass_kernel(int64_t n_seg, int f, const int64_t* __restrict_
                                 int* status) {
     const int gpb = blockDim.x / G;
     const int gl = threadIdx.x % G;
-    const int gbase = (threadIdx.x % 32) / G * G;
-    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gbase);
     const int64_t seg = blockIdx.x * (int64_t)gpb + threadIdx.x / G;
-    if (seg >= n_seg) return;  // whole groups exit together
+    if (seg >= n_seg) return;
     const int64_t b = seg_ptr[seg], e = seg_ptr[seg + 1];
     const double* myrow = mine_old + (size_t)seg * f;
     constexpr int MAXS = 8;  // factors per lane: f <= 32*8
+    constexpr int UN = 4;
     double num[MAXS], den[MAXS];
 #pragma unroll
     for (int s = 0; s < MAXS; ++s) num[s] = den[s] = 0.0;
-    for (int64_t a = b; a < e; ++a) {
-        const double* orow = other_old + (size_t)other_idx[a] * f;
-        const double r = r_seg[a];
-        double est;
-        if (est_seg) est = est_seg[a];
-        else est = ordered_dot<G>(myrow, orow, f, gl, gmask, gbase);  // mu = bu = bi = 0: est == dot
+    if (f <= G) {
+        // common case (one factor per lane): keep everything in registers
+        const bool act = gl < f;
+        double n0 = 0.0, d0 = 0.0;
+        int64_t a = b;
+        for (; a + UN <= e; a += UN) {
+            double o[UN], rr[UN], ee[UN];
 #pragma unroll
-        for (int s = 0; s < MAXS; ++s) {
-            const int j = gl + s * G;
-            if (j < f) {
-                const double o = orow[j];
-                num[s] = __dadd_rn(num[s], __dmul_rn(o, r));
-                den[s] = __dadd_rn(den[s], __dmul_rn(o, est));
+            for (int t = 0; t < UN; ++t) {
+                const int32_t oi = other_idx[a + t];
+                rr[t] = r_seg[a + t];
+                ee[t] = est_seg[a + t];
+                o[t] = act ? other_old[(size_t)oi * f + gl] : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < UN; ++t) {
+                n0 = __dadd_rn(n0, __dmul_rn(o[t], rr[t]));
+                d0 = __dadd_rn(d0, __dmul_rn(o[t], ee[t]));
+            }
+        }
+        for (; a < e; ++a) {
+            const double o = act ? other_old[(size_t)other_idx[a] * f + gl] : 0.0;
+            n0 = __dadd_rn(n0, __dmul_rn(o, r_seg[a]));
+            d0 = __dadd_rn(d0, __dmul_rn(o, est_seg[a]));
+        }
+        num[0] = n0;
+        den[0] = d0;
+    } else {
+        for (int64_t a = b; a < e; ++a) {
+            const double* orow = other_old + (size_t)other_idx[a] * f;
+            const double r = r_seg[a], est = est_seg[a];
+#pragma unroll
+            for (int s = 0; s < MAXS; ++s) {
+                const int j = gl + s * G;
+                if (j < f) {
+                    const double o = orow[j];
+                    num[s] = __dadd_rn(num[s], __dmul_rn(o, r));
+                    den[s] = __dadd_rn(den[s], __dmul_rn(o, est));
+                }
             }
         }
     }
@@ -309,29 +321,29 @@ int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, c
     }
     SB2_TRY(pu2.alloc((size_t)n_users * f * 8, st));
     SB2_TRY(qi2.alloc((size_t)n_items * f * 8, st));
-    if (biased) {
-        SB2_TRY(dot_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-        SB2_TRY(est_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-        SB2_TRY(est_it.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-    }
+    SB2_TRY(dot_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+    SB2_TRY(est_it.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+    if (biased) SB2_TRY(est_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
 
     double* pu_cur = pu;
     double* pu_nxt = pu2.as<double>();
     double* qi_cur = qi;
     double* qi_nxt = qi2.as<double>();
     for (int ep = 0; ep < prm->n_epochs; ++ep) {
-        const double* est_u = nullptr;
-        const double* est_i = nullptr;
-        if (biased && n > 0) {
+        const double* est_u = dot_d.as<double>();
+        const double* est_i = est_it.as<double>();
+        if (n > 0) {
             nmf_dot_kernel<<<nb, 256, 0, st>>>(n, f, u, i, pu_cur, qi_cur, dot_d.as<double>());
             SB2_LAUNCH_CHECK();
-            nmf_bias_scan_kernel<<<1, 32, 0, st>>>(n, u, i, r, dot_d.as<double>(), mu, prm->lr_bu, prm->lr_bi,
-                                                   prm->reg_bu, prm->reg_bi, bu, bi, est_d.as<double>());
+            if (biased) {
+                nmf_bias_scan_kernel<<<1, 32, 0, st>>>(n, u, i, r, dot_d.as<double>(), mu, prm->lr_bu, prm->lr_bi,
+                                                       prm->reg_bu, prm->reg_bi, bu, bi, est_d.as<double>());
+                SB2_LAUNCH_CHECK();
+                est_u = est_d.as<double>();
+            }
+            // unbiased: est == dot exactly (mu = bu = bi = 0 and 0 + x == x)
+            gather_f64_kernel<<<nb, 256, 0, st>>>(n, perm.as<int64_t>(), est_u, est_it.as<double>());
             SB2_LAUNCH_CHECK();
-            gather_f64_kernel<<<nb, 256, 0, st>>>(n, perm.as<int64_t>(), est_d.as<double>(), est_it.as<double>());
-            SB2_LAUNCH_CHECK();
-            est_u = est_d.as<double>();
-            est_i = est_it.as<double>();
         }
         SB2_TRY(nmf_pass(n_users, f, ptr_u.as<int64_t>(), i, r, est_u, pu_cur, qi_cur, pu_nxt, prm->reg_pu,
                          status_d.as<int>(), st));
