@@ -12,6 +12,7 @@
 // quantised to 47-bit fixed point and digit-split the same way; the b_x terms are applied in the fp64
 // finalize kernel.  See DESIGN.md "Similarity path" for the algebra and the error bound.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -359,7 +360,7 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
                     if (!full || cb >= rb) tiles.push_back(make_int2(rb, cb));
     }
     DevBuf tiles_d;
-    SB2_TRY(tiles_d.alloc(tiles.size() * sizeof(int2), st));
+    SB2_TRY(tiles_d.alloc(tiles.size() * sizeof(int2) + 16, st));
     SB2_CUDA(cudaMemcpyAsync(tiles_d.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
 
     // ---- planes + jobs ------------------------------------------------------------------------
@@ -413,9 +414,27 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
         }
         for (int s = nc - 1; s >= 0; --s) add(P_T2, M, pa.c_panel[s], ldexp(1.0, 8 * s + 48 - 2 * FB));
     }
+    const bool timing = getenv("SB2_SIM_TIMING") != nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (timing) {
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, st);
+    }
     if (!tiles.empty())
         SB2_TRY(gemm_u8_tc_run(jobs.data(), (int)jobs.size(), n_pad, k_pad, tiles_d.as<int2>(), (int)tiles.size(), ld,
                                row_begin, st));
+    if (timing) {
+        cudaEventRecord(ev1, st);
+        cudaEventSynchronize(ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        const double ops = 2.0 * (double)jobs.size() * (double)tiles.size() * GEMM_BM * GEMM_BN * (double)k_pad;
+        fprintf(stderr, "[sb2] sim gemm: %d accumulators x %zu tiles x k=%lld: %.3f ms, %.1f TOP/s issued\n",
+                (int)jobs.size(), tiles.size(), (long long)k_pad, ms, ops / (ms * 1e-3) / 1e12);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
 
     // ---- finalize -----------------------------------------------------------------------------
     FinArgs f;
