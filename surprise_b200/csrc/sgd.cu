@@ -38,7 +38,9 @@ struct DsgdArgs {
     int n_users, n_items, B, W, f, FP;  // FP = n_factors rounded up to 4
     int max_ul, max_il;                 // rows per user / item block (ceil)
     int US;                             // user row stride: FP (SVD) or 3*FP (SVD++: [p | z | g], see below)
-    int s_begin, s_end;                 // strata of this launch (SVD: all B; SVD++: one chunk)
+    int C;                              // CTAs per thread-block cluster (1 = no clusters); B = K * C
+    int ibuf;                           // floats per item-block buffer in shared memory
+    int s_begin, s_end;                 // OUTER steps of this launch (SVD: all K = B / C; SVD++: one chunk)
     int rec_cap;                        // records of a cell staged in shared memory
     const int* ul;                      // records grouped by cell (stratum-major), colour-sorted inside a cell
     const int* il;
@@ -67,6 +69,22 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(r)
+                 : "r"((uint32_t)__cvta_generic_to_shared(local_smem)), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 template <bool SMEM>
 __device__ __forceinline__ float4 row_ld4(const float* p) {
     if (SMEM) return *reinterpret_cast<const float4*>(p);
@@ -89,8 +107,9 @@ __device__ __forceinline__ void sc_st(float* p, float v) {
 }
 
 // one rating update by a group of G lanes (all lanes hold the same ul / il / r).
-// FAST: n_factors <= 4 * G, one 128-bit chunk per lane, the rows stay in registers between the dot
-// product and the update.  Otherwise lanes stride over the chunks and re-read the rows.
+// FAST: n_factors <= 16 * G, four 128-bit chunks per lane, the rows stay in registers between the dot product
+// and the update (few lanes per rating = many ratings per warp instruction: the update phase is bound by
+// instruction issue, profiles/r1_summary.md).  Otherwise 32 lanes stride over the chunks and re-read the rows.
 // PP (SVD++): the user row is [p | z | g]: z = sum_{j in I_u} y_j / sqrt|I_u| as of the last y_j application,
 // advanced by the user's own updates (z += lr_yj (err q - reg_yj z), which is exactly what the reference's
 // per-rating y_j updates do to that sum); g accumulates err * q / sqrt|I_u| for the next y_j application.
@@ -99,15 +118,23 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
                                            const float* isqp, float* cntp, float r, int gl, unsigned gmask, int F4) {
     const int FP = F4 * 4;
     if (FAST) {
-        const bool act = gl < F4;
+        // CH = 4 chunks of 128 bits per lane: chunk index gl + c * G
+        constexpr int CH = 4;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 p = zero4, q = zero4, z = zero4, g = zero4;
-        if (act) {
-            p = row_ld4<SU>(prow + 4 * gl);
-            q = row_ld4<SI>(qrow + 4 * gl);
-            if (PP) {
-                z = row_ld4<SU>(prow + FP + 4 * gl);
-                g = row_ld4<SU>(prow + 2 * FP + 4 * gl);
+        float4 p[CH], q[CH], z[CH], g[CH];
+        bool act[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int ch = gl + c * G;
+            act[c] = ch < F4;
+            p[c] = q[c] = z[c] = g[c] = zero4;
+            if (act[c]) {
+                p[c] = row_ld4<SU>(prow + 4 * ch);
+                q[c] = row_ld4<SI>(qrow + 4 * ch);
+                if (PP) {
+                    z[c] = row_ld4<SU>(prow + FP + 4 * ch);
+                    g[c] = row_ld4<SU>(prow + 2 * FP + 4 * ch);
+                }
             }
         }
         float b_u = 0.f, b_i = 0.f, isq = 0.f, cnt = 0.f;
@@ -119,33 +146,44 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
             isq = sc_ld<SU>(isqp);
             cnt = sc_ld<SU>(cntp);
         }
-        const float4 pz = PP ? make_float4(p.x + z.x, p.y + z.y, p.z + z.z, p.w + z.w) : p;
-        float dot = (pz.x * q.x + pz.y * q.y) + (pz.z * q.z + pz.w * q.w);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (PP) { p[c].x += z[c].x; p[c].y += z[c].y; p[c].z += z[c].z; p[c].w += z[c].w; }  // p <- p + z
+            dot += (p[c].x * q[c].x + p[c].y * q[c].y) + (p[c].z * q[c].z + p[c].w * q[c].w);
+        }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
         const float err = BIASED ? r - (a.mu + b_u + b_i + dot) : r - dot;
-        if (act) {
+        const float eg = err * isq;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (!act[c]) continue;
+            const int ch = gl + c * G;
+            const float4 pz = p[c];  // p (+ z for SVD++)
+            float4 po = pz;
+            if (PP) { po.x -= z[c].x; po.y -= z[c].y; po.z -= z[c].z; po.w -= z[c].w; }
             float4 pn, qn;
-            pn.x = p.x + a.lr_pu * (err * q.x - a.reg_pu * p.x);
-            pn.y = p.y + a.lr_pu * (err * q.y - a.reg_pu * p.y);
-            pn.z = p.z + a.lr_pu * (err * q.z - a.reg_pu * p.z);
-            pn.w = p.w + a.lr_pu * (err * q.w - a.reg_pu * p.w);
-            qn.x = q.x + a.lr_qi * (err * pz.x - a.reg_qi * q.x);
-            qn.y = q.y + a.lr_qi * (err * pz.y - a.reg_qi * q.y);
-            qn.z = q.z + a.lr_qi * (err * pz.z - a.reg_qi * q.z);
-            qn.w = q.w + a.lr_qi * (err * pz.w - a.reg_qi * q.w);
-            row_st4<SU>(prow + 4 * gl, pn);
-            row_st4<SI>(qrow + 4 * gl, qn);
+            pn.x = po.x + a.lr_pu * (err * q[c].x - a.reg_pu * po.x);
+            pn.y = po.y + a.lr_pu * (err * q[c].y - a.reg_pu * po.y);
+            pn.z = po.z + a.lr_pu * (err * q[c].z - a.reg_pu * po.z);
+            pn.w = po.w + a.lr_pu * (err * q[c].w - a.reg_pu * po.w);
+            qn.x = q[c].x + a.lr_qi * (err * pz.x - a.reg_qi * q[c].x);
+            qn.y = q[c].y + a.lr_qi * (err * pz.y - a.reg_qi * q[c].y);
+            qn.z = q[c].z + a.lr_qi * (err * pz.z - a.reg_qi * q[c].z);
+            qn.w = q[c].w + a.lr_qi * (err * pz.w - a.reg_qi * q[c].w);
+            row_st4<SU>(prow + 4 * ch, pn);
+            row_st4<SI>(qrow + 4 * ch, qn);
             if (PP) {
-                const float eg = err * isq;
                 float4 zn, gn;
-                zn.x = z.x + a.lr_yj * (err * q.x - a.reg_yj * z.x);
-                zn.y = z.y + a.lr_yj * (err * q.y - a.reg_yj * z.y);
-                zn.z = z.z + a.lr_yj * (err * q.z - a.reg_yj * z.z);
-                zn.w = z.w + a.lr_yj * (err * q.w - a.reg_yj * z.w);
-                gn.x = g.x + eg * q.x; gn.y = g.y + eg * q.y; gn.z = g.z + eg * q.z; gn.w = g.w + eg * q.w;
-                row_st4<SU>(prow + FP + 4 * gl, zn);
-                row_st4<SU>(prow + 2 * FP + 4 * gl, gn);
+                zn.x = z[c].x + a.lr_yj * (err * q[c].x - a.reg_yj * z[c].x);
+                zn.y = z[c].y + a.lr_yj * (err * q[c].y - a.reg_yj * z[c].y);
+                zn.z = z[c].z + a.lr_yj * (err * q[c].z - a.reg_yj * z[c].z);
+                zn.w = z[c].w + a.lr_yj * (err * q[c].w - a.reg_yj * z[c].w);
+                gn.x = g[c].x + eg * q[c].x; gn.y = g[c].y + eg * q[c].y;
+                gn.z = g[c].z + eg * q[c].z; gn.w = g[c].w + eg * q[c].w;
+                row_st4<SU>(prow + FP + 4 * ch, zn);
+                row_st4<SU>(prow + 2 * FP + 4 * ch, gn);
             }
         }
         if (gl == 0) {
@@ -219,7 +257,7 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
 
 // G lanes per rating, SU / SI: user / item block staged in shared memory, BIASED: SVD(biased=True)
 template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
-__global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const DsgdArgs a) {
+__global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int B = a.B, W = a.W, FP = a.FP, F4 = a.FP >> 2;
     const int US = a.US, U4 = a.US >> 2;  // user rows: US floats ([p] or [p | z | g])
@@ -227,14 +265,14 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int gid = tid / G, gl = tid % G;
     const int gbase = (tid & 31) / G * G;
-    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << gbase);
+    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << gbase);
 
     // shared memory carve-up
+    // item-block buffers: [max_il x FP factors | max_il biases], two of them when blocks hop through DSMEM
     float* pu_s = smem_f;
-    float* qi_s = pu_s + (SU ? (size_t)a.max_ul * US : 0);
-    float* bu_s = qi_s + (SI ? (size_t)a.max_il * FP : 0);
-    float* bi_s = bu_s + (SU ? a.max_ul : 0);
-    float* isq_s = bi_s + (SI ? a.max_il : 0);
+    float* ibuf_s = pu_s + (SU ? (size_t)a.max_ul * US : 0);
+    float* bu_s = ibuf_s + (SI ? (size_t)(a.C > 1 ? 2 : 1) * a.ibuf : 0);
+    float* isq_s = bu_s + (SU ? a.max_ul : 0);
     float* cnt_s = isq_s + ((SU && PP) ? a.max_ul : 0);
     int* wave_s = reinterpret_cast<int*>(cnt_s + ((SU && PP) ? a.max_ul : 0));
     int* coff_s = wave_s + (NW + 1);          // [2 * B]: cell begin / end per stratum
@@ -264,108 +302,139 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
     }
     __syncthreads();
 
-    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, t_proc = 0, n_proc = 0, n_wave = 0;
-    const int n_strata = a.s_end - a.s_begin;
+    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, t_proc = 0, n_proc = 0, n_wave = 0, t_hop = 0;
+    // Two-level ring.  CTAs form clusters of C; cluster Cl owns user blocks Cl*C .. Cl*C+C-1.  Item blocks form
+    // K = B / C super-blocks of C blocks.  Outer step T: super-block D = (Cl + T) % K is resident in the
+    // cluster; inner step t: CTA c updates item block (D, (c + t) % C) and then pushes it into its left
+    // neighbour's spare buffer through distributed shared memory (two cluster barriers, no global traffic).
+    // Only the K hand-offs between clusters go through L2 with the release / acquire step counters.
+    const int C = a.C, K = B / C;
+    const int Cl = ub / C, c = ub - Cl * C;
+    const int n_outer = a.s_end - a.s_begin;
+    int slot = 0;
     for (int ep = 0; ep < a.n_epochs; ++ep) {
-        for (int s = a.s_begin; s < a.s_end; ++s) {
-            const int ib = (ub + s) % B;
-            const int step = ep * n_strata + (s - a.s_begin);
-            const long long c0 = clock64();
-            // this stratum's records and wave table do not depend on the ring: fetch them while waiting
-            const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
-            const int staged = min(cnt, a.rec_cap);
-            for (int t = tid; t < staged; t += nthr) {
-                rul_s[t] = a.ul[k0 + t];
-                ril_s[t] = a.il[k0 + t];
-                rr_s[t] = a.r[k0 + t];
-            }
-            for (int t = tid; t <= NW; t += nthr) wave_s[t] = a.wave_off[((size_t)s * B + ub) * (NW + 1) + t];
-            if (tid == 0) {
-                while (ld_relaxed(a.flags + ib) != step) { /* ring neighbour still owns the block */ }
-                fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
-            }
-            __syncthreads();
-            const long long c1 = clock64();
-            const int ni_local = (a.n_items - ib + B - 1) / B;
-            if (SI) {
-                const int total = ni_local * F4;
-                for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
-                    float4 v[4];
+        for (int T = a.s_begin; T < a.s_end; ++T) {
+            const int D = (Cl + T) % K;
+            const int gstep = ep * n_outer + (T - a.s_begin);
+            for (int t = 0; t < C; ++t) {
+                const int s = T * C + t;
+                int j = c + t;
+                if (j >= C) j -= C;
+                const int ib = D * C + j;
+                float* qi_s = ibuf_s + (size_t)slot * a.ibuf;
+                float* bi_s = qi_s + (size_t)a.max_il * FP;
+                const long long c0 = clock64();
+                // this stratum's records and wave table do not depend on the ring: fetch them while waiting
+                const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
+                const int staged = min(cnt, a.rec_cap);
+                for (int x = tid; x < staged; x += nthr) {
+                    rul_s[x] = a.ul[k0 + x];
+                    ril_s[x] = a.il[k0 + x];
+                    rr_s[x] = a.r[k0 + x];
+                }
+                for (int x = tid; x <= NW; x += nthr) wave_s[x] = a.wave_off[((size_t)s * B + ub) * (NW + 1) + x];
+                if (t == 0 && tid == 0) {
+                    while (ld_relaxed(a.flags + ib) != gstep) { /* previous cluster still owns the super-block */ }
+                    fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
+                }
+                __syncthreads();
+                const long long c1 = clock64();
+                const int ni_local = (a.n_items - ib + B - 1) / B;
+                if (SI && t == 0) {
+                    const int total = ni_local * F4;
+                    for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
+                        float4 v[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int t = t0 + j * nthr;
-                        if (t < total) {
-                            const int l = t / F4, c = t - l * F4;
-                            v[j] = __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + c);
+                        for (int q = 0; q < 4; ++q) {
+                            const int x = t0 + q * nthr;
+                            if (x < total) {
+                                const int l = x / F4, cc = x - l * F4;
+                                v[q] = __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int x = t0 + q * nthr;
+                            if (x < total) reinterpret_cast<float4*>(qi_s)[x] = v[q];
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int t = t0 + j * nthr;
-                        if (t < total) reinterpret_cast<float4*>(qi_s)[t] = v[j];
-                    }
-                }
-                for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
-                __syncthreads();
-            }
-            const long long c2 = clock64();
-
-            auto process = [&](int k) {
-                int ul, il;
-                float r;
-                if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
-                else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
-                float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
-                float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
-                float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
-                float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
-                const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
-                float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
-                sgd_update<G, FAST, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, gmask, F4);
-            };
-            for (int w = 0; w < NW - 1; ++w) {
-                const int wb = wave_s[w], we = wave_s[w + 1];
-                if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
-                for (int k = wb + gid; k < we; k += W) {
-                    const long long p0 = clock64();
-                    process(k);
-                    t_proc += clock64() - p0;
-                    ++n_proc;
-                }
-                ++n_wave;
-                __syncthreads();
-            }
-            {
-                const int wb = wave_s[NW - 1], we = wave_s[NW];
-                if (wb != we) {  // sequential tail (colour overflow), one lane-group replays it in order
-                    if (gid == 0)
-                        for (int k = wb; k < we; ++k) {
-                            process(k);
-                            __syncwarp(gmask);  // consecutive tail ratings may share a row
-                        }
+                    for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
                     __syncthreads();
                 }
-            }
-            const long long c3 = clock64();
-            if (SI) {
-                for (int l = tid / F4, c = tid % F4; l < ni_local; ) {
-                    __stcg(reinterpret_cast<float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + c,
-                           reinterpret_cast<const float4*>(qi_s)[l * F4 + c]);
-                    c += nthr % F4; l += nthr / F4;
-                    if (c >= F4) { c -= F4; ++l; }
+                const long long c2 = clock64();
+
+                auto process = [&](int k) {
+                    int ul, il;
+                    float r;
+                    if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
+                    else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
+                    float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
+                    float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
+                    float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
+                    float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
+                    const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
+                    float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
+                    sgd_update<G, FAST, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, gmask, F4);
+                };
+                for (int w = 0; w < NW - 1; ++w) {
+                    const int wb = wave_s[w], we = wave_s[w + 1];
+                    if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
+                    for (int k = wb + gid; k < we; k += W) {
+                        const long long p0 = clock64();
+                        process(k);
+                        t_proc += clock64() - p0;
+                        ++n_proc;
+                    }
+                    ++n_wave;
+                    __syncthreads();
                 }
-                if (BIASED)
-                    for (int l = tid; l < ni_local; l += nthr) __stcg(a.bi + ib + (size_t)l * B, bi_s[l]);
+                {
+                    const int wb = wave_s[NW - 1], we = wave_s[NW];
+                    if (wb != we) {  // sequential tail (colour overflow), one lane-group replays it in order
+                        if (gid == 0)
+                            for (int k = wb; k < we; ++k) {
+                                process(k);
+                                __syncwarp(gmask);  // consecutive tail ratings may share a row
+                            }
+                        __syncthreads();
+                    }
+                }
+                const long long c3 = clock64();
+                if (t + 1 < C) {
+                    // fast hop: everybody in the cluster is done with its block -> push mine to the left neighbour's
+                    // spare buffer -> everybody's pushes have landed -> swap buffers
+                    cluster_sync_all();
+                    const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
+                    const int n4 = a.ibuf >> 2;
+                    for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
+                    cluster_sync_all();
+                    slot ^= 1;
+                    t_hop += clock64() - c3;
+                } else {
+                    // slow hop: hand the block to the next cluster through L2
+                    if (SI) {
+                        for (int l = tid / F4, cc = tid % F4; l < ni_local; ) {
+                            __stcg(reinterpret_cast<float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc,
+                                   reinterpret_cast<const float4*>(qi_s)[l * F4 + cc]);
+                            cc += nthr % F4; l += nthr / F4;
+                            if (cc >= F4) { cc -= F4; ++l; }
+                        }
+                        if (BIASED)
+                            for (int l = tid; l < ni_local; l += nthr) __stcg(a.bi + ib + (size_t)l * B, bi_s[l]);
+                    }
+                    // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
+                    __syncthreads();
+                    if (tid == 0) st_release(a.flags + ib, gstep + 1);
+                    t_wb += clock64() - c3;
+                }
+                t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2;
             }
-            // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
-            __syncthreads();
-            if (tid == 0) st_release(a.flags + ib, step + 1);
-            t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2; t_wb += clock64() - c3;
         }
     }
+    if (C > 1) cluster_sync_all();  // no CTA leaves while a neighbour may still address its shared memory
     if (a.prof != nullptr && tid == 0) {
         a.prof[ub * 8 + 0] = t_wait; a.prof[ub * 8 + 1] = t_load; a.prof[ub * 8 + 2] = t_upd; a.prof[ub * 8 + 3] = t_wb;
-        a.prof[ub * 8 + 4] = t_proc; a.prof[ub * 8 + 5] = n_proc; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = 0;
+        a.prof[ub * 8 + 4] = t_proc; a.prof[ub * 8 + 5] = n_proc; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = t_hop;
     }
     if (SU) {
         for (int l = tid / U4, c = tid % U4; l < nu_local; ) {
@@ -384,7 +453,7 @@ __global__ void __launch_bounds__(FAST ? 1024 : 256, 1) dsgd_svd_kernel(const Ds
 // ------------------------------------------------------------------------------------------------
 // preparation kernels: cell key -> stable sort -> per-cell greedy edge colouring -> wave tables
 // ------------------------------------------------------------------------------------------------
-__global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int B,
+__global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int B, int C,
                                 int n_users, int n_items, unsigned* __restrict__ key, int* __restrict__ val,
                                 int* __restrict__ cnt, int* status) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -397,7 +466,11 @@ __global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const 
         return;
     }
     const int ub = uu % B, ibk = ii % B;
-    const int s = (ibk - ub + B) % B;
+    // stratum of the two-level ring: outer step T moves super-blocks between clusters, inner step t inside
+    const int K = B / C;
+    const int Cl = ub / C, c = ub % C, D = ibk / C, j = ibk % C;
+    const int T = (D - Cl + K) % K, t = (j - c + C) % C;
+    const int s = T * C + t;
     const unsigned cell = (unsigned)(s * B + ub);
     key[k] = cell;
     atomicAdd(&cnt[cell], 1);
@@ -553,6 +626,7 @@ struct sb2_svd_plan {
     size_t smem = 0;
     int *ul = nullptr, *il = nullptr, *off = nullptr, *wave_off = nullptr, *flags = nullptr;
     int rec_cap = 0, max_cell = 0;
+    int C = 1, ibuf = 0;  // cluster size, floats per item buffer
     float *r = nullptr, *pu = nullptr, *qi = nullptr, *bu = nullptr, *bi = nullptr;
     bool owns_factors = true;
     // SVD++ state
@@ -567,43 +641,68 @@ struct sb2_svd_plan {
 
 namespace sb2 {
 
-template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
-static int dsgd_launch_t(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
-    auto kern = dsgd_svd_kernel<G, FAST, SU, SI, BIASED, PP>;
-    SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    void* args[] = {(void*)&a};
-    SB2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(p->B), dim3(p->W * G), args, p->smem, st));
-    launch_counter()++;
-    return SB2_OK;
-}
+typedef void (*dsgd_kernel_t)(const DsgdArgs);
 
 template <int G, bool FAST>
-static int dsgd_launch_g(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
+static dsgd_kernel_t dsgd_kernel_g(const sb2_svd_plan* p) {
     // staging plans: both blocks in shared memory, item block only, or neither.  SVD++ is always biased.
     if (p->with_yj) {
-        if (p->stage_u && p->stage_i) return dsgd_launch_t<G, FAST, true, true, true, true>(p, a, st);
-        if (p->stage_i) return dsgd_launch_t<G, FAST, false, true, true, true>(p, a, st);
-        return dsgd_launch_t<G, FAST, false, false, true, true>(p, a, st);
+        if (p->stage_u && p->stage_i) return dsgd_svd_kernel<G, FAST, true, true, true, true>;
+        if (p->stage_i) return dsgd_svd_kernel<G, FAST, false, true, true, true>;
+        return dsgd_svd_kernel<G, FAST, false, false, true, true>;
     }
     const bool b = p->prm.biased != 0;
     if (p->stage_u && p->stage_i)
-        return b ? dsgd_launch_t<G, FAST, true, true, true, false>(p, a, st)
-                 : dsgd_launch_t<G, FAST, true, true, false, false>(p, a, st);
+        return b ? dsgd_svd_kernel<G, FAST, true, true, true, false> : dsgd_svd_kernel<G, FAST, true, true, false, false>;
     if (p->stage_i)
-        return b ? dsgd_launch_t<G, FAST, false, true, true, false>(p, a, st)
-                 : dsgd_launch_t<G, FAST, false, true, false, false>(p, a, st);
-    return b ? dsgd_launch_t<G, FAST, false, false, true, false>(p, a, st)
-             : dsgd_launch_t<G, FAST, false, false, false, false>(p, a, st);
+        return b ? dsgd_svd_kernel<G, FAST, false, true, true, false> : dsgd_svd_kernel<G, FAST, false, true, false, false>;
+    return b ? dsgd_svd_kernel<G, FAST, false, false, true, false> : dsgd_svd_kernel<G, FAST, false, false, false, false>;
+}
+
+static dsgd_kernel_t dsgd_kernel(const sb2_svd_plan* p) {
+    if (!p->fast) return dsgd_kernel_g<32, false>(p);
+    switch (p->G) {
+        case 1: return dsgd_kernel_g<1, true>(p);
+        case 2: return dsgd_kernel_g<2, true>(p);
+        case 4: return dsgd_kernel_g<4, true>(p);
+        case 8: return dsgd_kernel_g<8, true>(p);
+        case 16: return dsgd_kernel_g<16, true>(p);
+        default: return dsgd_kernel_g<32, true>(p);
+    }
+}
+
+static void dsgd_launch_config(const sb2_svd_plan* p, int n_blocks, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr,
+                               cudaStream_t st) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->gridDim = dim3(n_blocks);
+    cfg->blockDim = dim3(p->W * p->G);
+    cfg->dynamicSmemBytes = p->smem;
+    cfg->stream = st;
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeCooperative;  // every CTA must be resident: they wait on each other
+    attr[na].val.cooperative = 1;
+    ++na;
+    if (p->C > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = p->C;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg->attrs = attr;
+    cfg->numAttrs = na;
 }
 
 static int dsgd_launch(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
-    if (!p->fast) return dsgd_launch_g<32, false>(p, a, st);
-    switch (p->G) {
-        case 4: return dsgd_launch_g<4, true>(p, a, st);
-        case 8: return dsgd_launch_g<8, true>(p, a, st);
-        case 16: return dsgd_launch_g<16, true>(p, a, st);
-        default: return dsgd_launch_g<32, true>(p, a, st);
-    }
+    dsgd_kernel_t kern = dsgd_kernel(p);
+    SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    dsgd_launch_config(p, p->B, &cfg, attr, st);
+    void* args[] = {(void*)&a};
+    SB2_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, args));
+    launch_counter()++;
+    return SB2_OK;
 }
 
 static void free_async(void* q, cudaStream_t st) {
@@ -641,30 +740,98 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     p->FP = (int)round_up(f, 4);
     p->US = p->with_yj ? 3 * p->FP : p->FP;
     const int F4 = p->FP / 4;
-    // lanes per rating: the smallest power of two covering the row in 128-bit chunks (one chunk per lane,
-    // rows stay in registers); rows longer than 128 factors fall back to 32 lanes striding the row.
+    // lanes per rating: four 128-bit chunks per lane (rows stay in registers); rows longer than 128 factors
+    // fall back to 32 lanes striding the row.
     p->fast = F4 <= 32;
-    p->G = F4 <= 4 ? 4 : F4 <= 8 ? 8 : F4 <= 16 ? 16 : 32;
-    const int threads = p->fast ? 1024 : 256;
+    p->G = !p->fast ? 32 : F4 <= 4 ? 1 : F4 <= 8 ? 2 : F4 <= 16 ? 4 : 8;
+    if (const char* e = getenv("SB2_DSGD_LANES")) {
+        const int g = atoi(e);
+        if (p->fast && (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) && g * 4 >= F4) p->G = g;
+    }
+    const int threads = 256;
     p->W = threads / p->G;
     if (const char* e = getenv("SB2_DSGD_GROUPS")) {
         const int w = atoi(e);
-        if (w > 0 && w * p->G <= threads && (w * p->G) % 32 == 0) p->W = w;
+        if (w > 0 && w * p->G <= 256 && (w * p->G) % 32 == 0) p->W = w;
     }
-    // Number of blocks B (= CTAs = strata per epoch).  Every stratum pays a fixed ring hand-off latency
-    // (write-back, release, acquire, reload: ~7k cycles measured) on top of its waves, so B trades
-    // parallelism against hand-offs: aim for cells of ~10 waves x W ratings, capped by the SM count.
+    // Blocks B (= CTAs = strata per epoch) and cluster size C.  With thread-block clusters an item block hops
+    // CTA -> CTA through distributed shared memory (~1k cycles) and only every C-th hop goes through L2
+    // (~8k cycles), so small cells are affordable: B = K * C as large as the co-residency limit allows, but at
+    // least ~16 ratings per cell.  Without clusters (C = 1: rows too long for two smem buffers, or tiny inputs)
+    // every hop is an L2 hop and bigger cells win: B ~ sqrt(N / (10 W)).
     int B = sm_count();
-    const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
-    if (B > b_work) B = b_work;
-    if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
-        const int b = atoi(e);
-        if (b > 0 && b <= sm_count()) B = b;
+    int C = 1;
+    const int b_rows = (int)std::min<int64_t>(std::min(n_users, n_items), 1 << 20);
+    if (const char* e = getenv("SB2_DSGD_CLUSTER")) C = atoi(e);
+    else C = 8;
+    if (C != 1 && C != 2 && C != 4 && C != 8) C = 1;
+    {
+        const int b_cells = std::max(1, (int)sqrt((double)std::max<int64_t>(n, 1) / 16.0));
+        int b_lim = std::min(std::min(B, b_rows), b_cells);
+        if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
+            const int b = atoi(e);
+            if (b > 0 && b <= sm_count()) b_lim = std::min(b, b_rows);
+        }
+        while (C > 1 && b_lim < 2 * C) C >>= 1;  // at least two clusters, else fall back to smaller clusters
+        if (C > 1) {
+            B = b_lim / C * C;
+        } else {
+            const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
+            B = std::min(std::min(sm_count(), b_rows), b_work);
+            if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
+                const int b = atoi(e);
+                if (b > 0 && b <= sm_count()) B = std::min(b, b_rows);
+            }
+        }
     }
-    if (B > n_users) B = (int)n_users;
-    if (B > n_items) B = (int)n_items;
+    if (B < 1) B = 1;
     p->B = B;
-    const int max_ul = (int)ceil_div(n_users, B), max_il = (int)ceil_div(n_items, B);
+    p->C = C;
+    int max_ul = (int)ceil_div(n_users, B), max_il = (int)ceil_div(n_items, B);
+    const size_t budget = 200 * 1024;
+    auto plan_smem = [&](int Bc, int Cc, bool* st_i, bool* st_u, size_t* used, int* ibuf) {
+        const int mul = (int)ceil_div(n_users, Bc), mil = (int)ceil_div(n_items, Bc);
+        const size_t fixed = (size_t)(NW + 1 + 2 * Bc) * 4 + 64;
+        *ibuf = (int)round_up((int64_t)mil * (p->FP + 1), 4);
+        const size_t need_i = (size_t)(Cc > 1 ? 2 : 1) * *ibuf * sizeof(float) + 16;
+        const size_t need_u = (size_t)mul * (p->US + 3) * sizeof(float) + 16;
+        const size_t min_rec = 256 * 12;
+        *st_i = fixed + min_rec + need_i <= budget;
+        *st_u = *st_i && fixed + min_rec + need_i + need_u <= budget;
+        *used = fixed + (*st_i ? need_i : 0) + (*st_u ? need_u : 0);
+    };
+    size_t smem_used = 0;
+    plan_smem(B, C, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
+    if (C > 1) {
+        // clusters need the item block in shared memory (twice) and enough co-resident clusters
+        bool ok = p->stage_i;
+        if (ok) {
+            p->smem = smem_used + 256 * 12 + 64;
+            dsgd_kernel_t kern = dsgd_kernel(p);
+            int max_clusters = 0;
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute attr[2];
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 16 * 1024));
+            dsgd_launch_config(p, B, &cfg, attr, st);
+            cfg.dynamicSmemBytes = budget;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kern, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                max_clusters = 0;
+            }
+            if (max_clusters < 2) ok = false;
+            else if (B / C > max_clusters) B = max_clusters * C;
+        }
+        if (!ok) {
+            C = 1;
+            const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
+            B = std::min(std::min(sm_count(), b_rows), b_work);
+        }
+        p->B = B;
+        p->C = C;
+        max_ul = (int)ceil_div(n_users, B);
+        max_il = (int)ceil_div(n_items, B);
+        plan_smem(B, C, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
+    }
     const size_t n_cells = (size_t)B * B;
 
     auto fail = [&](int rc) { plan_free(p); return rc; };
@@ -731,7 +898,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     }
     if (n > 0) {
         const unsigned nb = (unsigned)ceil_div(n, 256);
-        dsgd_key_kernel<<<nb, 256, 0, st>>>(n, u, i, B, (int)n_users, (int)n_items, key, val, cnt, status);
+        dsgd_key_kernel<<<nb, 256, 0, st>>>(n, u, i, B, C, (int)n_users, (int)n_items, key, val, cnt, status);
         launch_counter()++;
         size_t t1 = tb;
         PREP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t1, key, key2, val, val2, (int)n, 0, end_bit, st));
@@ -816,28 +983,20 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         cleanup2();
         // y_j is applied `chunks` times per epoch: a popular item must not receive more than ~32 raters'
         // accumulated gradients in one step (tools/proto/svdpp_variants.py, DESIGN.md "SVD++")
-        p->chunks = std::max(1, std::min(B, (int)ceil_div(max_raters, 32)));
+        p->chunks = std::max(1, std::min(B / C, (int)ceil_div(max_raters, 32)));
         if (const char* e = getenv("SB2_SVDPP_CHUNKS")) {
             const int c = atoi(e);
-            if (c >= 1) p->chunks = std::min(c, B);
+            if (c >= 1) p->chunks = std::min(c, B / C);
         }
     }
-    // shared-memory plan: wave table + cell offsets, item block (moves every stratum), user block, then
-    // as many of a cell's records as still fit (the rest is read from global memory)
-    const size_t budget = 200 * 1024;
-    const size_t fixed = (size_t)(NW + 1 + 2 * B) * 4 + 64;
-    const size_t need_i = (size_t)max_il * (p->FP + 1) * sizeof(float) + 16;
-    const size_t need_u = (size_t)max_ul * (p->US + 3) * sizeof(float) + 16;
-    const size_t min_rec = 256 * 12;
-    p->stage_i = fixed + min_rec + need_i <= budget;
-    p->stage_u = p->stage_i && fixed + min_rec + need_i + need_u <= budget;
-    size_t used = fixed + (p->stage_i ? need_i : 0) + (p->stage_u ? need_u : 0);
+    // shared-memory plan: wave table + cell offsets, item buffer(s), user block, then as many of a cell's
+    // records as still fit (the rest is read from global memory)
     int rec_cap = std::max(status_h[1], 1);
-    rec_cap = (int)std::min<size_t>((size_t)rec_cap, (budget - used) / 12);
+    rec_cap = (int)std::min<size_t>((size_t)rec_cap, (budget - smem_used) / 12);
     rec_cap = (int)round_up(rec_cap, 4);
     p->rec_cap = rec_cap;
     p->max_cell = status_h[1];
-    p->smem = used + (size_t)rec_cap * 12 + 64;
+    p->smem = smem_used + (size_t)rec_cap * 12 + 64;
     *out = p;
     return SB2_OK;
 }
@@ -873,6 +1032,8 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     a.ul = p->ul; a.il = p->il; a.r = p->r; a.cell_off = p->off; a.wave_off = p->wave_off; a.rec_cap = p->rec_cap;
     a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags;
     a.isq = p->isq; a.cnt = p->cnt;
+    a.C = p->C; a.ibuf = p->ibuf;
+    const int K = p->B / p->C;
     const sb2_sgd_params& q = p->prm;
     a.mu = (q.biased || p->with_yj) ? (float)q.global_mean : 0.f;
     a.lr_bu = (float)q.lr_bu; a.lr_bi = (float)q.lr_bi; a.lr_pu = (float)q.lr_pu; a.lr_qi = (float)q.lr_qi;
@@ -880,7 +1041,7 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     a.lr_yj = (float)q.lr_yj; a.reg_yj = (float)q.reg_yj;
     a.prof = p->prof;
     if (!p->with_yj) {
-        a.n_epochs = n_epochs; a.s_begin = 0; a.s_end = p->B;
+        a.n_epochs = n_epochs; a.s_begin = 0; a.s_end = K;
         SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
         return dsgd_launch(p, a, st);
     }
@@ -889,8 +1050,8 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     for (int ep = 0; ep < n_epochs; ++ep)
         for (int c = 0; c < p->chunks; ++c) {
             a.n_epochs = 1;
-            a.s_begin = (int)((int64_t)p->B * c / p->chunks);
-            a.s_end = (int)((int64_t)p->B * (c + 1) / p->chunks);
+            a.s_begin = (int)((int64_t)K * c / p->chunks);
+            a.s_end = (int)((int64_t)K * (c + 1) / p->chunks);
             if (a.s_begin == a.s_end) continue;
             svdpp_user_refresh_kernel<<<ub, 256, 0, st>>>(p->n_users, p->FP, p->u_ptr, p->ui_idx, p->yj, p->isq, p->pu,
                                                           p->cnt);
