@@ -80,6 +80,26 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem, uint32_t 
                  : "r"((uint32_t)__cvta_generic_to_shared(local_smem)), "r"(cta_rank));
     return r;
 }
+__device__ __forceinline__ void mbar_init_cta(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+// arrive on an mbarrier that lives in ANOTHER CTA of the cluster (address from mapa), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "MBW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra MBW_DONE;\n\t"
+        "bra MBW_LOOP;\n\t"
+        "MBW_DONE:\n\t"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
@@ -115,7 +135,8 @@ __device__ __forceinline__ void sc_st(float* p, float v) {
 // per-rating y_j updates do to that sum); g accumulates err * q / sqrt|I_u| for the next y_j application.
 template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
 __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float* qrow, float* bup, float* bip,
-                                           const float* isqp, float* cntp, float r, int gl, unsigned gmask, int F4) {
+                                           const float* isqp, float* cntp, float r, int gl, bool valid, int F4) {
+    constexpr unsigned gmask = 0xFFFFFFFFu;  // callers keep whole warps converged (dummy ratings: valid == false)
     const int FP = F4 * 4;
     if (FAST) {
         // CH = 4 chunks of 128 bits per lane: chunk index gl + c * G
@@ -126,7 +147,7 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int ch = gl + c * G;
-            act[c] = ch < F4;
+            act[c] = valid && ch < F4;
             p[c] = q[c] = z[c] = g[c] = zero4;
             if (act[c]) {
                 p[c] = row_ld4<SU>(prow + 4 * ch);
@@ -186,7 +207,7 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
                 row_st4<SU>(prow + 2 * FP + 4 * ch, gn);
             }
         }
-        if (gl == 0) {
+        if (gl == 0 && valid) {
             if (BIASED) {
                 sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
                 sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
@@ -212,7 +233,7 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
         const float b_u = sc_ld<SU>(bup), b_i = sc_ld<SI>(bip);
         err = r - (a.mu + b_u + b_i + dot);
         __syncwarp(gmask);  // every lane has read the biases before the leader overwrites them
-        if (gl == 0) {
+        if (gl == 0 && valid) {
             sc_st<SU>(bup, b_u + a.lr_bu * (err - a.reg_bu * b_u));
             sc_st<SI>(bip, b_i + a.lr_bi * (err - a.reg_bi * b_i));
         }
@@ -224,10 +245,10 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
         eg = err * sc_ld<SU>(isqp);
         const float cnt = sc_ld<SU>(cntp);
         __syncwarp(gmask);
-        if (gl == 0) sc_st<SU>(cntp, cnt + 1.f);
+        if (gl == 0 && valid) sc_st<SU>(cntp, cnt + 1.f);
     }
 #pragma unroll 1
-    for (int c = gl; c < F4; c += G) {
+    for (int c = gl; c < F4 && valid; c += G) {
         const float4 p = row_ld4<SU>(prow + 4 * c), q = row_ld4<SI>(qrow + 4 * c);
         float4 pz = p, pn, qn;
         if (PP) {
@@ -264,8 +285,6 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     const int ub = blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int gid = tid / G, gl = tid % G;
-    const int gbase = (tid & 31) / G * G;
-    const unsigned gmask = (G == 32) ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << gbase);
 
     // shared memory carve-up
     // item-block buffers: [max_il x FP factors | max_il biases], two of them when blocks hop through DSMEM
@@ -280,6 +299,15 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     int* ril_s = rul_s + a.rec_cap;
     float* rr_s = reinterpret_cast<float*>(ril_s + a.rec_cap);
 
+    // ring mailboxes (clusters): bar_data = "my right neighbour's push has landed in my spare buffer",
+    // bar_free = "my left neighbour has finished reading the buffer I am about to overwrite"
+    // Two of each, used alternately (push number & 1): a neighbour can run one push ahead of the CTA that waits,
+    // and a single mbarrier cannot tell "one phase ahead" from "not yet" once two phases have completed.
+    __shared__ __align__(8) uint64_t ring_bar[4];  // [0,1] data, [2,3] free
+    if (tid == 0) {
+        for (int x = 0; x < 4; ++x) mbar_init_cta(&ring_bar[x], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int nu_local = (a.n_users - ub + B - 1) / B;
     if (SU) {
         for (int l = tid / U4, c = tid % U4; l < nu_local; ) {
@@ -302,7 +330,7 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     }
     __syncthreads();
 
-    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, t_proc = 0, n_proc = 0, n_wave = 0, t_hop = 0;
+    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, n_wave = 0, t_hop = 0;
     // Two-level ring.  CTAs form clusters of C; cluster Cl owns user blocks Cl*C .. Cl*C+C-1.  Item blocks form
     // K = B / C super-blocks of C blocks.  Outer step T: super-block D = (Cl + T) % K is resident in the
     // cluster; inner step t: CTA c updates item block (D, (c + t) % C) and then pushes it into its left
@@ -312,6 +340,13 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     const int Cl = ub / C, c = ub - Cl * C;
     const int n_outer = a.s_end - a.s_begin;
     int slot = 0;
+    uint32_t n_push = 0;  // pushes done so far (selects the mbarrier phases)
+    uint32_t left_data_bar = 0, right_free_bar = 0;  // remote addresses of ring_bar[0] (left) / ring_bar[2] (right)
+    if (C > 1) {
+        cluster_sync_all();  // every CTA's mailboxes are initialised before anybody arrives on them
+        left_data_bar = dsmem_addr(&ring_bar[0], (uint32_t)(c == 0 ? C - 1 : c - 1));
+        right_free_bar = dsmem_addr(&ring_bar[2], (uint32_t)(c + 1 == C ? 0 : c + 1));
+    }
     for (int ep = 0; ep < a.n_epochs; ++ep) {
         for (int T = a.s_begin; T < a.s_end; ++T) {
             const int D = (Cl + T) % K;
@@ -363,51 +398,61 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
                 }
                 const long long c2 = clock64();
 
-                auto process = [&](int k) {
-                    int ul, il;
-                    float r;
-                    if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
-                    else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
+                // every lane-group runs the same (CTA-uniform) number of rounds per wave, groups beyond the wave's
+                // end carry a dummy rating with all stores predicated off: control flow stays warp-uniform, so the
+                // shuffles can use the full-warp mask (a per-group mask costs MATCH / VOTE instructions per shuffle)
+                auto process = [&](int k, bool valid) {
+                    int ul = 0, il = 0;
+                    float r = 0.f;
+                    if (valid) {
+                        if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
+                        else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
+                    }
                     float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
                     float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
                     float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
                     float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
                     const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
                     float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
-                    sgd_update<G, FAST, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, gmask, F4);
+                    sgd_update<G, FAST, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, valid, F4);
                 };
                 for (int w = 0; w < NW - 1; ++w) {
                     const int wb = wave_s[w], we = wave_s[w + 1];
                     if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
-                    for (int k = wb + gid; k < we; k += W) {
-                        const long long p0 = clock64();
-                        process(k);
-                        t_proc += clock64() - p0;
-                        ++n_proc;
-                    }
+                    for (int k = wb; k < we; k += W) process(k + gid, k + gid < we);
                     ++n_wave;
                     __syncthreads();
                 }
                 {
                     const int wb = wave_s[NW - 1], we = wave_s[NW];
-                    if (wb != we) {  // sequential tail (colour overflow), one lane-group replays it in order
-                        if (gid == 0)
+                    if (wb != we) {  // sequential tail (colour overflow), the first warp replays it in order
+                        if (tid < 32)
                             for (int k = wb; k < we; ++k) {
-                                process(k);
-                                __syncwarp(gmask);  // consecutive tail ratings may share a row
+                                process(k, gid == 0);
+                                __syncwarp();  // consecutive tail ratings may share a row
                             }
                         __syncthreads();
                     }
                 }
                 const long long c3 = clock64();
                 if (t + 1 < C) {
-                    // fast hop: everybody in the cluster is done with its block -> push mine to the left neighbour's
-                    // spare buffer -> everybody's pushes have landed -> swap buffers
-                    cluster_sync_all();
+                    // fast hop (neighbour-to-neighbour, no cluster-wide barrier): once the left neighbour has finished
+                    // reading its spare buffer (its previous push), copy my block into it through distributed shared
+                    // memory, tell it the data is there, tell my right neighbour that my block buffer is reusable,
+                    // and wait for my right neighbour's push into my own spare buffer.
+                    if (n_push > 0 && tid == 0) mbar_wait_cluster(&ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
+                    __syncthreads();
                     const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
                     const int n4 = a.ibuf >> 2;
                     for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
-                    cluster_sync_all();
+                    __syncthreads();  // all of this CTA's remote stores precede thread 0's cluster-scope releases
+                    if (tid == 0) {
+                        mbar_arrive_remote(left_data_bar + 8u * (n_push & 1));
+                        mbar_arrive_remote(right_free_bar + 8u * (n_push & 1));
+                        mbar_wait_cluster(&ring_bar[n_push & 1], (n_push >> 1) & 1);
+                    }
+                    __syncthreads();
+                    ++n_push;
                     slot ^= 1;
                     t_hop += clock64() - c3;
                 } else {
@@ -434,7 +479,7 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     if (C > 1) cluster_sync_all();  // no CTA leaves while a neighbour may still address its shared memory
     if (a.prof != nullptr && tid == 0) {
         a.prof[ub * 8 + 0] = t_wait; a.prof[ub * 8 + 1] = t_load; a.prof[ub * 8 + 2] = t_upd; a.prof[ub * 8 + 3] = t_wb;
-        a.prof[ub * 8 + 4] = t_proc; a.prof[ub * 8 + 5] = n_proc; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = t_hop;
+        a.prof[ub * 8 + 4] = t_upd; a.prof[ub * 8 + 5] = n_wave; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = t_hop;
     }
     if (SU) {
         for (int l = tid / U4, c = tid % U4; l < nu_local; ) {
@@ -679,9 +724,15 @@ static void dsgd_launch_config(const sb2_svd_plan* p, int n_blocks, cudaLaunchCo
     cfg->dynamicSmemBytes = p->smem;
     cfg->stream = st;
     int na = 0;
-    attr[na].id = cudaLaunchAttributeCooperative;  // every CTA must be resident: they wait on each other
-    attr[na].val.cooperative = 1;
-    ++na;
+    // Every CTA must be resident: they wait on each other.  Without clusters the cooperative-launch attribute
+    // guarantees it.  With clusters the grid is capped at cudaOccupancyMaxActiveClusters instead: the combination
+    // cooperative + cluster launch fails under Nsight Compute (LaunchFailed), and a kernel that cannot be
+    // profiled is not acceptable here.  SB2_DSGD_COOP=1 forces the attribute for cluster launches too.
+    if (p->C == 1 || getenv("SB2_DSGD_COOP") != nullptr) {
+        attr[na].id = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    }
     if (p->C > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = p->C;

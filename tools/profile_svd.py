@@ -33,6 +33,6 @@ tot = prof[:, :4].sum(1)
 m = prof.mean(0)
 print("per-CTA cycles (mean over CTAs) wait %.0f load %.0f update %.0f writeback %.0f  total %.0f; per stratum: %s"
       % (*m[:4], tot.mean(), np.round(m[:4] / (20 * b.value))))
-print("group0: %.0f cycles per update (%.1f updates/stratum); %.1f waves/stratum; update-phase cycles per wave %.0f"
-      % (m[4] / max(m[5], 1), m[5] / (20 * b.value), m[6] / (20 * b.value), m[2] / max(m[6], 1)))
+print("%.1f waves/stratum; update-phase cycles per wave %.0f; DSMEM hop cycles per stratum %.0f"
+      % (m[6] / (20 * b.value), m[2] / max(m[6], 1), m[7] / (20 * b.value)))
 lib.sb2_svd_plan_destroy(plan)
