@@ -147,3 +147,40 @@ class RingSVD(object):
         for p in self.plans:
             self.nat.lib().sb2_svd_plan_destroy(p)
         self.plans = []
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Row-block sharded similarity build: every rank packs the (replicated) rating CSR and
+# builds rows [row_begin, row_end) of the n_x x n_x matrix; there is no data-path collective.  Row blocks are
+# multiples of the 128-row MMA tile.
+# ------------------------------------------------------------------------------------------------------------
+def sim_row_range(n_x, rank, world, tile=128):
+    """Contiguous, tile-aligned row range of `rank` (balanced in tiles)."""
+    n_tiles = (n_x + tile - 1) // tile
+    lo = (n_tiles * rank) // world
+    hi = (n_tiles * (rank + 1)) // world
+    return min(lo * tile, n_x), min(hi * tile, n_x)
+
+
+def sim_build_sharded(dist, kind, n_x, yr, min_support, gather=False, **kw):
+    """Returns (row_begin, row_end, block) with block a CUDA float64 tensor (row_end-row_begin) x n_x; with
+    gather=True every rank also receives the full matrix (all_gather over NCCL), returned instead of the block."""
+    from . import similarities as sims
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    b, e = sim_row_range(n_x, rank, world)
+    torch = sims.nat.torch_cuda()
+    if e > b:
+        block = sims.build_device(kind, n_x, yr, min_support, row_begin=b, row_end=e, **kw)
+    else:
+        block = torch.empty((0, n_x), dtype=torch.float64, device=sims.nat.device())
+    if not gather or world == 1:
+        return b, e, block
+    ranges = [sim_row_range(n_x, r, world) for r in range(world)]
+    rows_max = max(hi - lo for lo, hi in ranges)
+    pad = torch.zeros((rows_max, n_x), dtype=torch.float64, device=block.device)
+    pad[:e - b] = block
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    full = torch.cat([parts[r][:hi - lo] for r, (lo, hi) in enumerate(ranges)], dim=0)
+    return 0, n_x, full

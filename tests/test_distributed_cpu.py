@@ -109,3 +109,11 @@ def test_ring_two_ranks_equals_replay(tmp_path):
         got = np.load(os.path.join(str(tmp_path), "r%d.npz" % g))
         assert np.array_equal(got["pu"], pu[g]) and np.array_equal(got["bu"], bu[g])
         assert np.array_equal(got["qi"], qi[g]) and np.array_equal(got["bi"], bi[g])
+
+
+def test_sim_row_ranges_cover_and_align():
+    for n_x, world in ((1187, 2), (27000, 8), (100, 4), (128, 3), (8192, 8)):
+        rows = [D.sim_row_range(n_x, r, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == n_x
+        for (lo, hi), (lo2, _) in zip(rows, rows[1:]):
+            assert hi == lo2 and lo % 128 == 0 and lo <= hi
