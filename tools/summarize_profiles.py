@@ -1,0 +1,71 @@
+"""Copy the judged artefacts from gpurun_out/ into profiles/ and regenerate profiles/r1_summary.md."""
+import collections, csv, json, os, shutil, subprocess, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
+def cp(src, dst):
+    if os.path.exists(os.path.join(G, src)):
+        shutil.copyfile(os.path.join(G, src), os.path.join(P, dst))
+cp("bench_launches.csv", "r1_bench_n1_launches.csv"); cp("bench_n1.json", "r1_bench_n1.json"); cp("bench_n2.json", "r1_bench_n2.json")
+cp("configs.json", "r1_configs_full_shape.json")
+out = []
+def launch_summary(f, title):
+    f = os.path.join(P, f)
+    if not os.path.exists(f): return
+    rows = [r for r in csv.reader(open(f)) if len(r) > 10]
+    hdr = rows[0]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try: v = float(r[vi].replace(',', ''))
+        except ValueError: continue
+        k = r[ki].split('(')[0][:80]
+        a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    out.append('## %s\n(ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES)\n' % title)
+    out.append('total %.3f ms over %d launches\n' % (tot / 1e6, sum(a[0] for a in agg.values())))
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
+        out.append('    %-82s n=%3d  %10.3f ms  %5.1f%%' % (k, c, t / 1e6, 100 * t / tot))
+    out.append('')
+def raw(rep, want, title):
+    rep = os.path.join(G, rep)
+    if not os.path.exists(rep): return
+    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    if len(rows) < 3: return
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    out.append('## %s\n(ncu --set full --clock-control none; kernel: %s)\n' % (title, dict(zip(hdr, vals)).get('Kernel Name', '?')[:100]))
+    for h, u, v in zip(hdr, units, vals):
+        if h in want: out.append('    %-72s %-16s %s' % (h, u, v))
+    out.append('')
+def stalls(rep, title):
+    rep = os.path.join(G, rep)
+    if not os.path.exists(rep): return
+    txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, data = rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    st = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+    tot = sum(int(r[ix['# Samples']] or 0) for r in data)
+    out.append('## %s: warp-stall samples (source page)\n' % title)
+    for s, v in sorted(((s, sum(int(r[ix[s]] or 0) for r in data)) for s in st), key=lambda kv: -kv[1])[:8]:
+        out.append('    %-28s %8d %5.1f%%' % (s, v, 100 * v / max(tot, 1)))
+    out.append('    top instructions:')
+    for r in sorted(data, key=lambda r: -int(r[ix['# Samples']] or 0))[:8]:
+        out.append('      %-60s samples=%s' % (r[ix['Source']][:60], r[ix['# Samples']]))
+    out.append('')
+launch_summary('r1_bench_n1_launches.csv', 'bench.py --steps 2 --warmup 3 (SVD config 2): every launch')
+launch_summary('r1_sim_cosine_launches.csv', 'tools/profile_sim.py cosine, 8192 items x 32768 users, 4M half-star ratings, 3 builds')
+launch_summary('r1_sim_pearson_baseline_launches.csv', 'tools/profile_sim.py pearson_baseline, same shape, 3 builds')
+W = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__registers_per_thread', 'launch__grid_size',
+     'launch__block_size', 'launch__cluster_size', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'lts__t_sectors.sum',
+     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+     'l1tex__m_xbar2l1tex_read_bytes.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum.per_second',
+     'TPC.TriageCompute.sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg', 'sm__cycles_active.avg',
+     'lts__throughput.avg.pct_of_peak_sustained_elapsed']
+raw('svd_prof.ncu-rep', W, 'dsgd_svd_kernel, 20 epochs of the bench workload in one launch')
+stalls('svd_prof.ncu-rep', 'dsgd_svd_kernel')
+raw('gemm_prof.ncu-rep', W, 'gemm_u8_tc_kernel (tcgen05 kind::i8), cosine batch: 4 accumulators, 3+3 panels, 2080 tiles x 512 k-blocks')
+for f in ('sweep2.log', 'sweep3.log'):
+    pass
+open(os.path.join(P, 'r1_summary.md'), 'w').write('# Round 1 profile summaries (B200, sm_100a)\n\nRaw artefacts next to this file: r1_*_launches.csv (ncu launch lists), r1_bench_n1.json / r1_bench_n2.json (bench lines of\nthe same build), r1_configs_full_shape.json (BASELINE.json configs 3-5 at full shape on one GPU), r1_dsgd_*.log\n(in-kernel phase counters, sb2_svd_plan_profile).\n\n' + '\n'.join(out))
+print('\n'.join(out)[:3000])
