@@ -66,7 +66,8 @@ void sb2_reset_launch_count(void);
  * floating point in the reference too and matches it to ~1e-12 absolute (contract: 1e-9).
  *
  * Rows [row_begin, row_end) of the n_x x n_x matrix are produced into sim_out (row-major,
- * (row_end-row_begin) x n_x): the row-block shard of one rank.  row_begin = 0, row_end = n_x builds
+ * (row_end-row_begin) x n_x): the row-block shard of one rank (row_begin a multiple of 256, the tile of the
+ * CTA-pair MMA kernel).  row_begin = 0, row_end = n_x builds
  * the whole matrix and exploits symmetry.  x_biases / y_biases / global_mean / shrinkage are only
  * read for SB2_SIM_PEARSON_BASELINE (min_support is clamped to >= 2 there, similarities.pyx:334).
  * The _dev form synchronises `stream` once to read the duplicate / zero-division status.
@@ -82,7 +83,7 @@ int sb2_sim_build(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
 
 /* Test hook: C[m x n] (int32, row-major, ld = n) = A[m x k] * B[n x k]^T for u8 operands through the
  * tcgen05 kernel (use_tensor_cores = 1) or through the scalar dp4a cross-check kernel (0).
- * m, n multiples of 128, k multiple of 64.  Device pointers. */
+ * m, n multiples of 256, k multiple of 128.  Device pointers. */
 int sb2_gemm_u8_selftest_dev(int use_tensor_cores, int64_t m, int64_t n, int64_t k, const uint8_t* a,
                              const uint8_t* b, int32_t* c, void* stream);
 

@@ -254,13 +254,14 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
     }
     if (pb && min_support < 2) min_support = 2;  // similarities.pyx:334
     const bool full = (row_begin == 0 && row_end == n_x);
-    if (!full && row_begin % GEMM_BM) {
-        set_error("sim_build: row_begin of a shard must be a multiple of %d", GEMM_BM);
+    const int TR = gemm_tile_rows();  // 256 (CTA-pair kernel) or 128
+    if (!full && row_begin % TR) {
+        set_error("sim_build: row_begin of a shard must be a multiple of %d", TR);
         return SB2_ERR_INVALID;
     }
-    const int64_t n_pad = round_up(n_x, GEMM_BM);
-    const int64_t k_pad = round_up(std::max<int64_t>(n_y, 1), GEMM_BK);
-    const int64_t rows_pad = round_up(row_end, GEMM_BM) - row_begin;  // plane rows (shard)
+    const int64_t n_pad = round_up(n_x, TR);
+    const int64_t k_pad = round_up(std::max<int64_t>(n_y, 1), GEMM_BK);  // 128
+    const int64_t rows_pad = round_up(row_end, TR) - row_begin;  // plane rows (shard)
     const int64_t ld = n_pad;
 
     // ---- pass 1: analyse ratings --------------------------------------------------------------
@@ -351,9 +352,9 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
     // tiles in flight share ~12 A-side and ~12 B-side row blocks of every panel (L2 reuse).
     std::vector<int2> tiles;
     {
-        const int rb0 = (int)(row_begin / GEMM_BM), rb1 = (int)ceil_div(row_end, GEMM_BM);
-        const int ncb = (int)(n_pad / GEMM_BN);
-        const int band = 12;
+        const int rb0 = (int)(row_begin / TR), rb1 = (int)ceil_div(row_end, TR);
+        const int ncb = (int)(n_pad / TR);
+        const int band = TR == 256 ? 8 : 12;
         for (int b0 = rb0; b0 < rb1; b0 += band)
             for (int cb = 0; cb < ncb; ++cb)
                 for (int rb = b0; rb < std::min(b0 + band, rb1); ++rb)
@@ -429,7 +430,7 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
         cudaEventSynchronize(ev1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
-        const double ops = 2.0 * (double)jobs.size() * (double)tiles.size() * GEMM_BM * GEMM_BN * (double)k_pad;
+        const double ops = 2.0 * (double)jobs.size() * (double)tiles.size() * TR * TR * (double)k_pad;
         fprintf(stderr, "[sb2] sim gemm: %d accumulators x %zu tiles x k=%lld: %.3f ms, %.1f TOP/s issued\n",
                 (int)jobs.size(), tiles.size(), (long long)k_pad, ms, ops / (ms * 1e-3) / 1e12);
         cudaEventDestroy(ev0);

@@ -152,9 +152,9 @@ class RingSVD(object):
 # ------------------------------------------------------------------------------------------------------------
 # Row-block sharded similarity build: every rank packs the (replicated) rating CSR and
 # builds rows [row_begin, row_end) of the n_x x n_x matrix; there is no data-path collective.  Row blocks are
-# multiples of the 128-row MMA tile.
+# multiples of the 256-row tile of the CTA-pair MMA kernel.
 # ------------------------------------------------------------------------------------------------------------
-def sim_row_range(n_x, rank, world, tile=128):
+def sim_row_range(n_x, rank, world, tile=256):
     """Contiguous, tile-aligned row range of `rank` (balanced in tiles)."""
     n_tiles = (n_x + tile - 1) // tile
     lo = (n_tiles * rank) // world

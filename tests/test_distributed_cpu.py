@@ -116,4 +116,4 @@ def test_sim_row_ranges_cover_and_align():
         rows = [D.sim_row_range(n_x, r, world) for r in range(world)]
         assert rows[0][0] == 0 and rows[-1][1] == n_x
         for (lo, hi), (lo2, _) in zip(rows, rows[1:]):
-            assert hi == lo2 and lo % 128 == 0 and lo <= hi
+            assert hi == lo2 and lo % 256 == 0 and lo <= hi

@@ -34,7 +34,7 @@ def test_device_is_blackwell():
     assert maj.value == 10, "kernels are built for sm_100a only"
 
 
-@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 1024), (512, 128, 4096 + 64)])
+@pytest.mark.parametrize("shape", [(256, 256, 128), (256, 512, 1024), (768, 256, 4096 + 128)])
 def test_tcgen05_gemm_against_dp4a_and_numpy(shape):
     import torch
     m, n, k = shape
@@ -113,7 +113,7 @@ def test_u1_row_shard_equals_full(u1):
     full = sims.cosine(ts.n_items, yr, 1)
     for kind in ("cosine", "pearson"):
         full = getattr(sims, kind)(ts.n_items, yr, 1)
-        for (b, e) in ((0, 128), (128, 512), (1152, ts.n_items)):
+        for (b, e) in ((0, 256), (256, 768), (1024, ts.n_items)):
             blk = sims.build_device(kind, ts.n_items, yr, 1, row_begin=b, row_end=e).cpu().numpy()
             assert np.array_equal(blk, full[b:e]), (kind, b, e)
 
