@@ -212,7 +212,9 @@ int sb2_mf_predict(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t 
  * Batched k-NN estimate.  Replaces KNNBasic.estimate (knns.py:99-123) and KNNBaseline.estimate
  * (:274-309): gather sim[x, x2] over yr[y], stable top-k (heapq.nlargest semantics), ordered fp64
  * weighted sum -- bit-identical to the reference.
- * mode: 0 = KNNBasic; 1 = KNNBaseline with x = user (user_based); 2 = KNNBaseline with x = item.
+ * mode: 0 = KNNBasic; 1 = KNNBaseline with x = user (user_based); 2 = KNNBaseline with x = item;
+ *       3 = KNNWithMeans (knns.py:178-208; bx = means[n_x], by unused); 4 = KNNWithZScore (:372-403; bx = means,
+ *       by = sigmas, both indexed by x).
  * x[k] / y[k] < 0 = unknown.  actual_k[k] = -1 where the reference reports no actual_k.
  * impossible[k]: 1 = PredictionImpossible, 2 = the reference would raise ZeroDivisionError.
  * sim: n_x x n_x row-major with leading dimension sim_ld (>= n_x).

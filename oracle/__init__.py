@@ -214,7 +214,8 @@ def mf_estimate(u, i, biased, global_mean, pu, qi, bu, bi, yj=None, u_ptr=None, 
 
 
 def knn_estimate(x, y, sim, y_ptr, x_idx, r, k, min_k, baseline=0, global_mean=0.0, bx=None, by=None):
-    """baseline: 0 = KNNBasic, 1 = KNNBaseline with x = user, 2 = KNNBaseline with x = item."""
+    """baseline: 0 = KNNBasic, 1 / 2 = KNNBaseline with x = user / item, 3 = KNNWithMeans (bx = means),
+    4 = KNNWithZScore (bx = means, by = sigmas, both per x)."""
     x, y = _i32(x), _i32(y)
     sim = _f64(sim)
     y_ptr, x_idx, r = _i64(y_ptr), _i32(x_idx), _f64(r)

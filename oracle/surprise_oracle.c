@@ -10,10 +10,9 @@
  * -O2 -ffp-contract=off (the reference's Cython C is built with plain gcc -O2: strict IEEE fp64,
  * no FMA contraction), so results are meant to be BIT-IDENTICAL to the Cython build.
  *
- * Parity pin: oracle/check_oracle_vs_ref.py runs this file against the compiled reference
- * (oracle/_ref, built by oracle/build_ref.sh) on the reference's own fixtures, and
- * tests/test_oracle.py checks it against the golden vectors committed under tests/golden/
- * (generated from the compiled reference by tests/golden/make_golden.py).
+ * Parity pin: tests/test_oracle.py checks this file bit for bit against the golden vectors committed
+ * under tests/golden/, which tests/golden/make_golden.py generated from the compiled, unmodified
+ * reference (oracle/_ref, built by oracle/build_ref.sh) on the reference's own fixtures.
  *
  * Data layout (flat, mirrors what the reference's dict-of-lists iteration visits):
  *   "yr" CSR : y_ptr[n_y+1], x_idx[N], r[N]   -- for y in yr (insertion order), for (x, r) in yr[y]
@@ -426,6 +425,8 @@ int orc_mf_estimate(int64_t n_pairs, const int32_t *u, const int32_t *i, int f, 
  * baseline != 0: est = mu + bx[x] + by[y] (+ weighted residual mean), never impossible when both known.
  * Unknown ids (x<0 or y<0): basic -> impossible; baseline -> partial baseline, actual_k = -1
  * (the reference returns a bare float there, knns.py:285-286, so `details` has no actual_k).
+ * baseline == 3: KNNWithMeans (knns.py:178-208), bx = means[n_x];  baseline == 4: KNNWithZScore (:372-403),
+ * bx = means, by = sigmas (both indexed by x).
  * ------------------------------------------------------------------------------------------ */
 typedef struct { double s; double r; int32_t nb; int32_t pos; } orc_nb_t;
 
@@ -448,7 +449,10 @@ int orc_knn_estimate(int64_t n_pairs, const int32_t *x, const int32_t *y, int64_
         const int kx = x[p] >= 0, ky = y[p] >= 0;
         impossible[p] = 0;
         actual_k[p] = -1;
-        if (baseline) {
+        if (baseline >= 3) {
+            if (!(kx && ky)) { impossible[p] = 1; est[p] = 0.0; continue; }
+            est[p] = bx[x[p]];
+        } else if (baseline) {
             double e = global_mean;
             /* est += bu[u]; est += bi[i] in that order (user first).  The caller passes bx/by
              * already switched, so it must also say which of them is the user side; to stay
@@ -483,7 +487,11 @@ int orc_knn_estimate(int64_t n_pairs, const int32_t *x, const int32_t *y, int64_
         for (int64_t a = 0; a < top; ++a) {
             if (buf[a].s > 0) {
                 sum_sim += buf[a].s;
-                if (baseline) {
+                if (baseline == 3) {
+                    sum_r += buf[a].s * (buf[a].r - bx[buf[a].nb]);
+                } else if (baseline == 4) {
+                    sum_r += buf[a].s * (buf[a].r - bx[buf[a].nb]) / by[buf[a].nb];
+                } else if (baseline) {
                     const double nb_bsl = global_mean + bx[buf[a].nb] + by[y[p]];
                     sum_r += buf[a].s * (buf[a].r - nb_bsl);
                 } else {
@@ -495,7 +503,10 @@ int orc_knn_estimate(int64_t n_pairs, const int32_t *x, const int32_t *y, int64_
         actual_k[p] = ak;
         if (baseline) {
             if (ak < min_k) sum_r = 0.0;
-            if (ak > 0) est[p] += sum_r / sum_sim; /* ZeroDivisionError swallowed, knns.py:303-306 */
+            if (ak > 0) { /* ZeroDivisionError swallowed otherwise, knns.py:303-306 / :203-206 / :398-401 */
+                if (baseline == 4) est[p] += sum_r / sum_sim * by[x[p]];
+                else est[p] += sum_r / sum_sim;
+            }
         } else {
             if (ak < min_k) { impossible[p] = 1; est[p] = 0.0; continue; }
             if (ak == 0) { impossible[p] = 2; est[p] = 0.0; continue; } /* min_k<=0: 0/0 raises */

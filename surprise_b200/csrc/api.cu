@@ -510,19 +510,19 @@ int sb2_knn_predict(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
     SB2_TRY(upload(d_idx, x_idx, (size_t)nnz, st));
     SB2_TRY(upload(d_r, r, (size_t)nnz, st));
     if (mode != 0) {
-        if (!bx || !by) {
-            set_error("knn_predict: baselines required for mode != 0");
+        if (!bx || (mode != 3 && !by)) {
+            set_error("knn_predict: per-x / per-y vectors required for this mode");
             return SB2_ERR_INVALID;
         }
         SB2_TRY(upload(d_bx, bx, (size_t)n_x, st));
-        SB2_TRY(upload(d_by, by, (size_t)n_y, st));
+        if (by) SB2_TRY(upload(d_by, by, (size_t)(mode == 4 ? n_x : n_y), st));
     }
     SB2_TRY(d_est.alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8, st));
     SB2_TRY(d_ak.alloc((size_t)std::max<int64_t>(n_pairs, 1) * 4, st));
     SB2_TRY(d_imp.alloc((size_t)std::max<int64_t>(n_pairs, 1), st));
     SB2_TRY(knn_predict_dev(n_pairs, d_x.as<int32_t>(), d_y.as<int32_t>(), n_x, d_sim.as<double>(), n_x,
                             d_ptr.as<int64_t>(), d_idx.as<int32_t>(), d_r.as<double>(), k, min_k, mode, global_mean,
-                            mode ? d_bx.as<double>() : nullptr, mode ? d_by.as<double>() : nullptr, d_est.as<double>(),
+                            mode ? d_bx.as<double>() : nullptr, (mode && by) ? d_by.as<double>() : nullptr, d_est.as<double>(),
                             d_ak.as<int32_t>(), d_imp.as<uint8_t>(), st));
     SB2_TRY(download(est, d_est.p, (size_t)n_pairs, st));
     SB2_TRY(download(actual_k, d_ak.p, (size_t)n_pairs, st));

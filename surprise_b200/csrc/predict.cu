@@ -94,15 +94,16 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
         double e = 0.0;
         int ak = -1;
         uint8_t imp = 0;
-        if (mode != 0) {
+        if (mode == 1 || mode == 2) {
             e = mu;
             // est += bu[u] first, then bi[i] (knns.py:276-280); mode 1: x is the user, mode 2: y is
             if (mode == 1) { if (kx) e = __dadd_rn(e, bx[xx]); if (ky) e = __dadd_rn(e, by[yy]); }
             else { if (ky) e = __dadd_rn(e, by[yy]); if (kx) e = __dadd_rn(e, bx[xx]); }
         }
         if (!(kx && ky)) {
-            if (mode == 0) imp = 1;
+            if (mode == 0 || mode >= 3) imp = 1;  // KNNBasic / WithMeans / WithZScore raise PredictionImpossible
         } else {
+            if (mode >= 3) e = bx[xx];  // means[x] (knns.py:187, :382)
             const int64_t b = y_ptr[yy], len = y_ptr[yy + 1] - b;
             const double* srow = sim + (size_t)xx * (size_t)sim_ld;
             const bool cached = len <= KNN_CACHE;
@@ -138,7 +139,12 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
                 if (!(bs > 0.0)) break;  // everything that follows is <= 0 and contributes nothing
                 const double rr = r[b + bp];
                 sum_sim = __dadd_rn(sum_sim, bs);
-                if (mode != 0) {
+                if (mode == 3) {
+                    sum_r = __dadd_rn(sum_r, __dmul_rn(bs, __dsub_rn(rr, bx[x_idx[b + bp]])));
+                } else if (mode == 4) {
+                    const int32_t nb = x_idx[b + bp];
+                    sum_r = __dadd_rn(sum_r, __ddiv_rn(__dmul_rn(bs, __dsub_rn(rr, bx[nb])), by[nb]));
+                } else if (mode != 0) {
                     const double nb_bsl = __dadd_rn(__dadd_rn(mu, bx[x_idx[b + bp]]), by[yy]);
                     sum_r = __dadd_rn(sum_r, __dmul_rn(bs, __dsub_rn(rr, nb_bsl)));
                 } else {
@@ -148,7 +154,10 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
             }
             if (mode != 0) {
                 if (ak < min_k) sum_r = 0.0;
-                if (ak > 0) e = __dadd_rn(e, __ddiv_rn(sum_r, sum_sim));  // ZeroDivisionError swallowed otherwise
+                if (ak > 0) {  // ZeroDivisionError swallowed otherwise
+                    if (mode == 4) e = __dadd_rn(e, __dmul_rn(__ddiv_rn(sum_r, sum_sim), by[xx]));
+                    else e = __dadd_rn(e, __ddiv_rn(sum_r, sum_sim));
+                }
             } else {
                 if (ak < min_k) imp = 1;       // PredictionImpossible('Not enough neighbors.')
                 else if (ak == 0) imp = 2;     // min_k <= 0: the reference divides 0 / 0
@@ -169,7 +178,7 @@ int knn_predict_dev(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
                     int mode, double mu, const double* bx, const double* by, double* est, int32_t* actual_k,
                     uint8_t* impossible, cudaStream_t st) {
     if (n_pairs <= 0) return SB2_OK;
-    if (mode < 0 || mode > 2 || (mode != 0 && (!bx || !by))) {
+    if (mode < 0 || mode > 4 || (mode != 0 && !bx) || ((mode == 1 || mode == 2 || mode == 4) && !by)) {
         set_error("knn_predict: invalid mode / missing baselines");
         return SB2_ERR_INVALID;
     }

@@ -1,4 +1,5 @@
-"""k-NN algorithms (reference: prediction_algorithms/knns.py:20-309): KNNBasic and KNNBaseline.
+"""k-NN algorithms (reference: prediction_algorithms/knns.py:20-403): KNNBasic, KNNWithMeans, KNNBaseline,
+KNNWithZScore.
 
 fit() builds the similarity matrix on the device (tensor-core contractions) and keeps it there;
 test() ships all known (x, y) pairs to the warp-select kernel (sb2_knn_predict_dev) which reproduces
@@ -161,4 +162,71 @@ class KNNBaseline(SymmetricAlgo):
             return est[0], {"actual_k": details[0]["actual_k"]}
         return est[0]
 
+    _batch_estimate_of = estimate
+
+
+def _row_stats(trainset, user_based, with_sigma):
+    """means[x] (and sigmas[x]) over xr[x] in list order with np.mean / np.std per row, as knns.py:168-170 and
+    :362-366 do (numpy's pairwise reduction over the same sequence => the same bits)."""
+    ptr, _, val = trainset.user_csr() if user_based else trainset.item_csr()
+    n_x = len(ptr) - 1
+    means = np.zeros(n_x)
+    sigmas = np.zeros(n_x) if with_sigma else None
+    for x in range(n_x):
+        row = val[ptr[x]:ptr[x + 1]]
+        means[x] = np.mean(row)
+        if with_sigma:
+            sigmas[x] = np.std(row)
+    return means, sigmas
+
+
+class _MeanCenteredKNN(SymmetricAlgo):
+    _mode = 3
+
+    def __init__(self, k=40, min_k=1, sim_options={}, **kwargs):
+        SymmetricAlgo.__init__(self, sim_options=sim_options, **kwargs)
+        self.k = k
+        self.min_k = min_k
+
+    def _estimate_batch(self, iu, ii):
+        est, ak, imp = self._knn_batch(iu, ii, self._mode, self.means, getattr(self, "sigmas", None))
+        details = [({"was_impossible": True, "reason": "User and/or item is unkown."} if imp[k]
+                    else {"actual_k": int(ak[k]), "was_impossible": False}) for k in range(len(est))]
+        return est, details
+
+    def estimate(self, u, i):
+        est, details = self._estimate_batch(np.array([_as_inner(u)], dtype=np.int32),
+                                            np.array([_as_inner(i)], dtype=np.int32))
+        if details[0]["was_impossible"]:
+            raise PredictionImpossible(details[0]["reason"])
+        return est[0], {"actual_k": details[0]["actual_k"]}
+
+
+class KNNWithMeans(_MeanCenteredKNN):
+    """knns.py:126-208.  est = mu_x + sum(sim * (r - mu_nb)) / sum(sim)."""
+    _mode = 3
+
+    def fit(self, trainset):
+        SymmetricAlgo.fit(self, trainset)
+        self._sim_dev = self.compute_similarities_device()
+        self.means, _ = _row_stats(trainset, self.sim_options["user_based"], False)
+        return self
+
+    estimate = _MeanCenteredKNN.estimate
+    _batch_estimate_of = estimate
+
+
+class KNNWithZScore(_MeanCenteredKNN):
+    """knns.py:312-403.  est = mu_x + sigma_x * sum(sim * (r - mu_nb) / sigma_nb) / sum(sim)."""
+    _mode = 4
+
+    def fit(self, trainset):
+        SymmetricAlgo.fit(self, trainset)
+        self.means, sigmas = _row_stats(trainset, self.sim_options["user_based"], True)
+        self.overall_sigma = np.std(trainset.user_csr()[2])  # all_ratings() order, knns.py:359-360
+        self.sigmas = np.where(sigmas == 0.0, self.overall_sigma, sigmas)
+        self._sim_dev = self.compute_similarities_device()
+        return self
+
+    estimate = _MeanCenteredKNN.estimate
     _batch_estimate_of = estimate

@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 
 ref = oracle.import_reference()
-from surprise import Dataset, Reader, KNNBasic, KNNBaseline, SVD, SVDpp, NMF, BaselineOnly, accuracy  # noqa: E402
+from surprise import Dataset, Reader, KNNBasic, KNNBaseline, KNNWithMeans, KNNWithZScore, SVD, SVDpp, NMF, BaselineOnly, accuracy  # noqa: E402
 from surprise import similarities as rsims  # noqa: E402
 from surprise.model_selection import PredefinedKFold  # noqa: E402
 
@@ -120,6 +120,10 @@ for ub in (False, True):
     run(KNNBaseline(sim_options={"name": "pearson_baseline", "user_based": ub}), "KNNBaseline_pb_" + o)
     run(KNNBaseline(k=10, min_k=3, sim_options={"name": "msd", "user_based": ub}), "KNNBaseline_msd_k10_mk3_" + o)
 run(KNNBasic(k=5, min_k=2, sim_options={"name": "msd", "user_based": True}), "KNNBasic_msd_k5_mk2_user")
+for ub in (False, True):
+    o = "user" if ub else "item"
+    run(KNNWithMeans(sim_options={"name": "msd", "user_based": ub}), "KNNWithMeans_msd_" + o)
+    run(KNNWithZScore(k=20, min_k=2, sim_options={"name": "pearson", "user_based": ub}), "KNNWithZScore_pearson_k20_mk2_" + o)
 
 svd, _ = run(SVD(random_state=0), "SVD_rs0")
 G["algos"]["SVD_rs0"]["pu_sha256"] = sha(svd.pu)

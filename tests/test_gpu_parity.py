@@ -260,6 +260,20 @@ def test_u1_knnbaseline_end_to_end(u1, u1_golden, u1_arrays, orient):
     assert abs(float(sb.accuracy.rmse(preds, verbose=False)) - float(u1_golden["algos"][tag]["rmse"])) < 1e-7
 
 
+@pytest.mark.parametrize("orient", ("item", "user"))
+def test_u1_knn_means_zscore_end_to_end(u1, u1_golden, u1_arrays, orient):
+    ts, testset = u1
+    ub = orient == "user"
+    for algo, tag in ((sb.KNNWithMeans(sim_options={"name": "msd", "user_based": ub}), "KNNWithMeans_msd_" + orient),
+                      (sb.KNNWithZScore(k=20, min_k=2, sim_options={"name": "pearson", "user_based": ub}),
+                       "KNNWithZScore_pearson_k20_mk2_" + orient)):
+        preds = algo.fit(ts).test(testset)
+        assert np.array_equal(np.array([p.est for p in preds]), u1_arrays[tag + "_est"]), tag
+        assert np.array_equal(np.array([p.details.get("actual_k", -1) for p in preds]), u1_arrays[tag + "_actual_k"])
+        assert repr(float(sb.accuracy.rmse(preds, verbose=False))) == u1_golden["algos"][tag]["rmse"]
+        assert sum(p.details["was_impossible"] for p in preds) == u1_golden["algos"][tag]["n_impossible"]
+
+
 def test_knn_long_lists_and_ties():
     """Lists longer than the per-warp cache and many tied similarities (stable selection order)."""
     rng = np.random.RandomState(1)
@@ -476,7 +490,7 @@ def test_unknown_user_or_item_and_pickle(tmp_path):
     reader = sb.Reader(line_format="user item rating", sep=" ", skip_lines=3, rating_scale=(1, 5))
     data = sb.Dataset.load_from_file(os.path.join(GOLDEN, "custom_dataset"), reader)
     ts = data.build_full_trainset()
-    for klass in (sb.SVD, sb.SVDpp, sb.NMF, sb.KNNBasic, sb.KNNBaseline, sb.BaselineOnly):
+    for klass in (sb.SVD, sb.SVDpp, sb.NMF, sb.KNNBasic, sb.KNNBaseline, sb.KNNWithMeans, sb.KNNWithZScore, sb.BaselineOnly):
         algo = klass()
         algo.fit(ts)
         algo.predict("user0", "unknown_item", None)

@@ -205,6 +205,32 @@ def test_u1_knn_estimates_bit_exact(u1, u1_golden, u1_arrays, orient):
     assert np.array_equal(ak, u1_arrays[tag + "_actual_k"])
 
 
+@pytest.mark.parametrize("orient", ("item", "user"))
+def test_u1_knn_means_zscore_bit_exact(u1, u1_arrays, orient):
+    """KNNWithMeans / KNNWithZScore (knns.py:126-208, :312-403): the "next" rows of SURVEY.md section 8f."""
+    from surprise_b200.prediction_algorithms.knns import _row_stats
+    ts, testset = u1
+    ub = orient == "user"
+    iu, ii = inner_pairs(ts, testset)
+    x, y = (iu, ii) if ub else (ii, iu)
+    n_x = ts.n_users if ub else ts.n_items
+    ptr, idx, val = ts.item_csr() if ub else ts.user_csr()
+    mu = float(ts.global_mean)
+    lo, hi = ts.rating_scale
+    means, sigmas = _row_stats(ts, ub, True)
+    sigmas = np.where(sigmas == 0.0, np.std(ts.user_csr()[2]), sigmas)
+    sim = oracle.similarity("msd", n_x, ptr, idx, val, 1)
+    est, ak, imp = oracle.knn_estimate(x, y, sim, ptr, idx, val, 40, 1, 3, mu, means, None)
+    tag = "KNNWithMeans_msd_" + orient
+    assert np.array_equal(np.clip(np.where(imp > 0, mu, est), lo, hi), u1_arrays[tag + "_est"])
+    assert np.array_equal(np.where(imp > 0, -1, ak), u1_arrays[tag + "_actual_k"])
+    sim = oracle.similarity("pearson", n_x, ptr, idx, val, 1)
+    est, ak, imp = oracle.knn_estimate(x, y, sim, ptr, idx, val, 20, 2, 4, mu, means, sigmas)
+    tag = "KNNWithZScore_pearson_k20_mk2_" + orient
+    assert np.array_equal(np.clip(np.where(imp > 0, mu, est), lo, hi), u1_arrays[tag + "_est"])
+    assert np.array_equal(np.where(imp > 0, -1, ak), u1_arrays[tag + "_actual_k"])
+
+
 def test_float_ratings_similarities(floats):
     """Jester-style float ratings: the oracle must reproduce the reference bit for bit here too."""
     import surprise_b200 as sb
