@@ -193,6 +193,22 @@ int sb2_nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* 
 int sb2_nmf_fit(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
                 const double* r, const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi);
 
+/* Epoch-at-a-time form for the multi-GPU fit (device pointers).  The plan holds what depends only on the rating
+ * structure; the COO arrays are borrowed and must outlive it.  One epoch restricted to users
+ * [user_begin, user_end) and items [item_begin, item_end) reads the full pu_cur / qi_cur and writes those rows
+ * of pu_new / qi_new: every ordered accumulator sum is evaluated on exactly one rank, so sharded results stay
+ * bit-identical; the caller all-gathers the new factors between epochs.  bu / bi (biased model) are advanced in
+ * place by the sequential recursion, which every rank replays.  sb2_nmf_plan_status synchronises the stream and
+ * reports SB2_ERR_ZERO_DIVISION / SB2_ERR_INVALID (input not grouped by user). */
+typedef struct sb2_nmf_plan sb2_nmf_plan;
+int sb2_nmf_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, int n_factors, void* stream, sb2_nmf_plan** out);
+int sb2_nmf_plan_epoch_dev(sb2_nmf_plan* plan, const sb2_nmf_params* prm, const double* pu_cur, const double* qi_cur,
+                           double* pu_new, double* qi_new, double* bu, double* bi, int64_t user_begin,
+                           int64_t user_end, int64_t item_begin, int64_t item_end, void* stream);
+int sb2_nmf_plan_status(sb2_nmf_plan* plan, void* stream);
+void sb2_nmf_plan_destroy(sb2_nmf_plan* plan);
+
 /* ------------------------------------------------------------------------------------------------
  * Batched estimate for the factor models.  Replaces SVD.estimate (matrix_factorization.pyx:269-299),
  * NMF.estimate (:737-761) and SVDpp.estimate (:506-522; yj != NULL) called once per pair by

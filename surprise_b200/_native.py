@@ -67,6 +67,10 @@ SIGNATURES = {
     "sb2_svdpp_fit": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_nmf_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_nmf_fit": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb2_nmf_plan_create_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp]),
+    "sb2_nmf_plan_epoch_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "sb2_nmf_plan_status": (_int, [_vp, _vp]),
+    "sb2_nmf_plan_destroy": (None, [_vp]),
     "sb2_mf_predict_dev": (_int, [_i64, _vp, _vp, _int, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp]),
     "sb2_mf_predict": (_int, [_i64, _vp, _vp, _i64, _i64, _int, _int, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

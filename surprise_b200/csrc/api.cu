@@ -9,6 +9,7 @@
 #include "sim_gemm.cuh"
 
 struct sb2_svd_plan;
+struct sb2_nmf_plan;
 
 namespace sb2 {
 
@@ -46,6 +47,13 @@ int baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t*
                      double mu, int n_epochs, double reg, double lr, double* bu, double* bi, cudaStream_t st);
 int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
                 const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi, cudaStream_t st);
+int nmf_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
+                        int n_factors, cudaStream_t st, sb2_nmf_plan** out);
+int nmf_plan_epoch_dev(sb2_nmf_plan* p, const sb2_nmf_params* prm, const double* pu_cur, const double* qi_cur,
+                       double* pu_new, double* qi_new, double* bu, double* bi, int64_t u0, int64_t u1, int64_t i0,
+                       int64_t i1, cudaStream_t st);
+int nmf_plan_status(sb2_nmf_plan* p, cudaStream_t st);
+void nmf_plan_destroy(sb2_nmf_plan* p);
 int mf_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int f, int biased, double mu, const double* pu,
                    const double* qi, const double* bu, const double* bi, const double* yj, const int64_t* u_ptr,
                    const int32_t* ui_idx, double* est, uint8_t* impossible, cudaStream_t st);
@@ -444,6 +452,20 @@ int sb2_nmf_fit(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, c
     SB2_CUDA(cudaStreamSynchronize(st));
     return SB2_OK;
 }
+
+int sb2_nmf_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, int n_factors, void* stream, sb2_nmf_plan** out) {
+    SB2_TRY(ensure_device());
+    return nmf_plan_create_dev(n_users, n_items, n, u, i, r, n_factors, (cudaStream_t)stream, out);
+}
+int sb2_nmf_plan_epoch_dev(sb2_nmf_plan* plan, const sb2_nmf_params* prm, const double* pu_cur, const double* qi_cur,
+                           double* pu_new, double* qi_new, double* bu, double* bi, int64_t user_begin,
+                           int64_t user_end, int64_t item_begin, int64_t item_end, void* stream) {
+    return nmf_plan_epoch_dev(plan, prm, pu_cur, qi_cur, pu_new, qi_new, bu, bi, user_begin, user_end, item_begin,
+                              item_end, (cudaStream_t)stream);
+}
+int sb2_nmf_plan_status(sb2_nmf_plan* plan, void* stream) { return nmf_plan_status(plan, (cudaStream_t)stream); }
+void sb2_nmf_plan_destroy(sb2_nmf_plan* plan) { nmf_plan_destroy(plan); }
 
 // ---- predict -----------------------------------------------------------------------------------
 int sb2_mf_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int n_factors, int biased,

@@ -7,7 +7,11 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <vector>
+
 #include "common.cuh"
+
+struct sb2_nmf_plan;
 
 namespace sb2 {
 
@@ -258,109 +262,172 @@ static int nmf_pass(int64_t n_seg, int f, const int64_t* ptr, const int32_t* idx
     return launch_pass<32>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
 }
 
-int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
-                const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi, cudaStream_t st) {
-    const int f = prm->n_factors;
-    if (f <= 0 || f > 256 || n_users <= 0 || n_items <= 0 || n < 0) {
-        set_error("nmf_fit: invalid shape (n_factors must be in [1, 256])");
+// est for a range of CSC (item-ordered) entries, recomputed from the factors: dot(q[item], p[user]) in factor
+// order -- the same multiply/add chain as nmf_dot_kernel, hence the same bits as est[perm[k]].
+__global__ void nmf_dot_item_kernel(int64_t e0, int64_t e1, int f, const int32_t* __restrict__ i_it,
+                                    const int32_t* __restrict__ u_it, const double* __restrict__ pu,
+                                    const double* __restrict__ qi, double* __restrict__ est_it) {
+    const int64_t k = e0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= e1) return;
+    const double* p = pu + (size_t)u_it[k] * f;
+    const double* q = qi + (size_t)i_it[k] * f;
+    double d = 0.0;
+    for (int j = 0; j < f; ++j) d = __dadd_rn(d, __dmul_rn(q[j], p[j]));
+    est_it[k] = d;
+}
+
+}  // namespace sb2
+
+// NMF plan: everything that depends only on the rating structure (user CSR offsets, item-side CSC by a
+// stable sort of positions) plus per-epoch scratch.  One epoch can be restricted to a user range and an item
+// range: the multi-GPU formulation shards the ACCUMULATORS (each ordered sum lives on exactly one rank, so the
+// result stays bit-exact) and all-gathers the new factors between epochs (surprise_b200/distributed.py).
+struct sb2_nmf_plan {
+    int64_t n_users = 0, n_items = 0, n = 0;
+    int f = 0;
+    const int32_t* u = nullptr;  // borrowed: the all_ratings COO must outlive the plan
+    const int32_t* i = nullptr;
+    const double* r = nullptr;
+    sb2::DevBuf status, ptr_u, ptr_i, perm, u_it, i_it, r_it, dot, est, est_it;
+    std::vector<int64_t> ptr_u_h, ptr_i_h;
+};
+
+namespace sb2 {
+
+int nmf_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
+                        int n_factors, cudaStream_t st, sb2_nmf_plan** out) {
+    const int f = n_factors;
+    if (f <= 0 || f > 256 || n_users <= 0 || n_items <= 0 || n < 0 || n > 0x7FFFFFF0ll) {
+        set_error("nmf_plan: invalid shape (n_factors must be in [1, 256])");
         return SB2_ERR_INVALID;
     }
-    const bool biased = prm->biased != 0;
-    const double mu = biased ? prm->global_mean : 0.0;
-
-    DevBuf status_d, cnt_u, cnt_i, ptr_u, ptr_i, perm, perm_in, keys_out, u_it, r_it, pu2, qi2, tmp, dot_d, est_d, est_it;
-    SB2_TRY(status_d.alloc(2 * sizeof(int), st));
-    SB2_CUDA(cudaMemsetAsync(status_d.p, 0, 2 * sizeof(int), st));
-    SB2_CUDA(cudaMemsetAsync(bu, 0, (size_t)n_users * sizeof(double), st));
-    SB2_CUDA(cudaMemsetAsync(bi, 0, (size_t)n_items * sizeof(double), st));
-    const unsigned nb = (unsigned)ceil_div(std::max<int64_t>(n, 1), 256);
-
+    sb2_nmf_plan* p = new sb2_nmf_plan();
+    struct Guard {
+        sb2_nmf_plan* p;
+        ~Guard() { delete p; }
+    } guard{p};
+    p->n_users = n_users; p->n_items = n_items; p->n = n; p->f = f; p->u = u; p->i = i; p->r = r;
+    DevBuf cnt_u, cnt_i, perm_in, tmp;
+    SB2_TRY(p->status.alloc(2 * sizeof(int), st));
+    SB2_CUDA(cudaMemsetAsync(p->status.p, 0, 2 * sizeof(int), st));
+    const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+    const unsigned nb = (unsigned)ceil_div((int64_t)n1, 256);
     // user CSR = the COO itself (grouped by u); item CSC = stable sort of positions by item
     SB2_TRY(cnt_u.alloc((size_t)(n_users + 1) * 8, st));
     SB2_TRY(cnt_i.alloc((size_t)(n_items + 1) * 8, st));
-    SB2_TRY(ptr_u.alloc((size_t)(n_users + 1) * 8, st));
-    SB2_TRY(ptr_i.alloc((size_t)(n_items + 1) * 8, st));
+    SB2_TRY(p->ptr_u.alloc((size_t)(n_users + 1) * 8, st));
+    SB2_TRY(p->ptr_i.alloc((size_t)(n_items + 1) * 8, st));
     SB2_CUDA(cudaMemsetAsync(cnt_u.p, 0, (size_t)(n_users + 1) * 8, st));
     SB2_CUDA(cudaMemsetAsync(cnt_i.p, 0, (size_t)(n_items + 1) * 8, st));
     if (n > 0) {
-        check_grouped_kernel<<<nb, 256, 0, st>>>(n, u, status_d.as<int>());
+        check_grouped_kernel<<<nb, 256, 0, st>>>(n, u, p->status.as<int>());
         SB2_LAUNCH_CHECK();
         count_kernel<<<nb, 256, 0, st>>>(n, u, cnt_u.as<unsigned long long>());
         SB2_LAUNCH_CHECK();
         count_kernel<<<nb, 256, 0, st>>>(n, i, cnt_i.as<unsigned long long>());
         SB2_LAUNCH_CHECK();
     }
-    {
-        size_t tb1 = 0, tb2 = 0, tb3 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb1, cnt_u.as<int64_t>(), ptr_u.as<int64_t>(), (int)(n_users + 1), st);
-        cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt_i.as<int64_t>(), ptr_i.as<int64_t>(), (int)(n_items + 1), st);
-        SB2_TRY(perm.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-        SB2_TRY(perm_in.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-        SB2_TRY(keys_out.alloc((size_t)std::max<int64_t>(n, 1) * 4, st));
-        cub::DeviceRadixSort::SortPairs(nullptr, tb3, i, keys_out.as<int32_t>(), perm_in.as<int64_t>(),
-                                        perm.as<int64_t>(), (int)n, 0, 32, st);
-        size_t tb = std::max(tb1, std::max(tb2, tb3));
-        SB2_TRY(tmp.alloc(tb + 16, st));
-        SB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_u.as<int64_t>(), ptr_u.as<int64_t>(), (int)(n_users + 1), st));
-        SB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_i.as<int64_t>(), ptr_i.as<int64_t>(), (int)(n_items + 1), st));
-        sb2::launch_counter() += 2;
-        if (n > 0) {
-            iota_kernel<<<nb, 256, 0, st>>>(n, perm_in.as<int64_t>());
-            SB2_LAUNCH_CHECK();
-            // LSD radix sort is stable: equal items keep all_ratings() order (u ascending, then ur[u] order)
-            SB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, i, keys_out.as<int32_t>(), perm_in.as<int64_t>(),
-                                                     perm.as<int64_t>(), (int)n, 0, 32, st));
-            sb2::launch_counter() += 1;
-        }
-    }
-    SB2_TRY(u_it.alloc((size_t)std::max<int64_t>(n, 1) * 4, st));
-    SB2_TRY(r_it.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+    size_t tb1 = 0, tb2 = 0, tb3 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb1, cnt_u.as<int64_t>(), p->ptr_u.as<int64_t>(), (int)(n_users + 1), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt_i.as<int64_t>(), p->ptr_i.as<int64_t>(), (int)(n_items + 1), st);
+    SB2_TRY(p->perm.alloc(n1 * 8, st));
+    SB2_TRY(perm_in.alloc(n1 * 8, st));
+    SB2_TRY(p->i_it.alloc(n1 * 4, st));
+    cub::DeviceRadixSort::SortPairs(nullptr, tb3, i, p->i_it.as<int32_t>(), perm_in.as<int64_t>(), p->perm.as<int64_t>(),
+                                    (int)n, 0, 32, st);
+    size_t tb = std::max(tb1, std::max(tb2, tb3));
+    SB2_TRY(tmp.alloc(tb + 16, st));
+    SB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_u.as<int64_t>(), p->ptr_u.as<int64_t>(), (int)(n_users + 1), st));
+    SB2_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_i.as<int64_t>(), p->ptr_i.as<int64_t>(), (int)(n_items + 1), st));
+    launch_counter() += 2;
+    SB2_TRY(p->u_it.alloc(n1 * 4, st));
+    SB2_TRY(p->r_it.alloc(n1 * 8, st));
     if (n > 0) {
-        gather_item_side_kernel<<<nb, 256, 0, st>>>(n, perm.as<int64_t>(), u, r, u_it.as<int32_t>(), r_it.as<double>());
+        iota_kernel<<<nb, 256, 0, st>>>(n, perm_in.as<int64_t>());
+        SB2_LAUNCH_CHECK();
+        // LSD radix sort is stable: equal items keep all_ratings() order (u ascending, then ur[u] order)
+        SB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, i, p->i_it.as<int32_t>(), perm_in.as<int64_t>(),
+                                                 p->perm.as<int64_t>(), (int)n, 0, 32, st));
+        launch_counter() += 1;
+        gather_item_side_kernel<<<nb, 256, 0, st>>>(n, p->perm.as<int64_t>(), u, r, p->u_it.as<int32_t>(),
+                                                    p->r_it.as<double>());
         SB2_LAUNCH_CHECK();
     }
-    SB2_TRY(pu2.alloc((size_t)n_users * f * 8, st));
-    SB2_TRY(qi2.alloc((size_t)n_items * f * 8, st));
-    SB2_TRY(dot_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-    SB2_TRY(est_it.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
-    if (biased) SB2_TRY(est_d.alloc((size_t)std::max<int64_t>(n, 1) * 8, st));
+    SB2_TRY(p->dot.alloc(n1 * 8, st));
+    SB2_TRY(p->est_it.alloc(n1 * 8, st));
+    p->ptr_u_h.resize((size_t)n_users + 1);
+    p->ptr_i_h.resize((size_t)n_items + 1);
+    SB2_CUDA(cudaMemcpyAsync(p->ptr_u_h.data(), p->ptr_u.p, (size_t)(n_users + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaMemcpyAsync(p->ptr_i_h.data(), p->ptr_i.p, (size_t)(n_items + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    guard.p = nullptr;
+    *out = p;
+    return SB2_OK;
+}
 
-    double* pu_cur = pu;
-    double* pu_nxt = pu2.as<double>();
-    double* qi_cur = qi;
-    double* qi_nxt = qi2.as<double>();
-    for (int ep = 0; ep < prm->n_epochs; ++ep) {
-        const double* est_u = dot_d.as<double>();
-        const double* est_i = est_it.as<double>();
-        if (n > 0) {
-            nmf_dot_kernel<<<nb, 256, 0, st>>>(n, f, u, i, pu_cur, qi_cur, dot_d.as<double>());
+// One epoch restricted to users [u0, u1) and items [i0, i1): reads pu_cur / qi_cur (full), writes the rows of
+// pu_new / qi_new in the ranges.  bu / bi are updated in place when biased (sequential recursion, replicated).
+int nmf_plan_epoch_dev(sb2_nmf_plan* p, const sb2_nmf_params* prm, const double* pu_cur, const double* qi_cur,
+                       double* pu_new, double* qi_new, double* bu, double* bi, int64_t u0, int64_t u1, int64_t i0,
+                       int64_t i1, cudaStream_t st) {
+    if (u0 < 0 || u1 > p->n_users || u0 > u1 || i0 < 0 || i1 > p->n_items || i0 > i1 || prm->n_factors != p->f) {
+        set_error("nmf_epoch: invalid range / n_factors");
+        return SB2_ERR_INVALID;
+    }
+    const int f = p->f;
+    const int64_t n = p->n;
+    const bool biased = prm->biased != 0;
+    const double mu = biased ? prm->global_mean : 0.0;
+    const bool full = (u0 == 0 && u1 == p->n_users && i0 == 0 && i1 == p->n_items);
+    const int64_t eu0 = p->ptr_u_h[(size_t)u0], eu1 = p->ptr_u_h[(size_t)u1];
+    const int64_t ei0 = p->ptr_i_h[(size_t)i0], ei1 = p->ptr_i_h[(size_t)i1];
+    const double* est_u = p->dot.as<double>();
+    if (n > 0) {
+        if (biased) {
+            if (!p->est.p) SB2_TRY(p->est.alloc((size_t)n * 8, st));
+            const unsigned nb = (unsigned)ceil_div(n, 256);
+            nmf_dot_kernel<<<nb, 256, 0, st>>>(n, f, p->u, p->i, pu_cur, qi_cur, p->dot.as<double>());
             SB2_LAUNCH_CHECK();
-            if (biased) {
-                nmf_bias_scan_kernel<<<1, 32, 0, st>>>(n, u, i, r, dot_d.as<double>(), mu, prm->lr_bu, prm->lr_bi,
-                                                       prm->reg_bu, prm->reg_bi, bu, bi, est_d.as<double>());
-                SB2_LAUNCH_CHECK();
-                est_u = est_d.as<double>();
-            }
+            nmf_bias_scan_kernel<<<1, 32, 0, st>>>(n, p->u, p->i, p->r, p->dot.as<double>(), mu, prm->lr_bu, prm->lr_bi,
+                                                   prm->reg_bu, prm->reg_bi, bu, bi, p->est.as<double>());
+            SB2_LAUNCH_CHECK();
+            est_u = p->est.as<double>();
+            gather_f64_kernel<<<nb, 256, 0, st>>>(n, p->perm.as<int64_t>(), est_u, p->est_it.as<double>());
+            SB2_LAUNCH_CHECK();
+        } else {
             // unbiased: est == dot exactly (mu = bu = bi = 0 and 0 + x == x)
-            gather_f64_kernel<<<nb, 256, 0, st>>>(n, perm.as<int64_t>(), est_u, est_it.as<double>());
-            SB2_LAUNCH_CHECK();
+            if (eu1 > eu0) {
+                nmf_dot_kernel<<<(unsigned)ceil_div(eu1 - eu0, 256), 256, 0, st>>>(eu1 - eu0, f, p->u + eu0, p->i + eu0,
+                                                                                  pu_cur, qi_cur, p->dot.as<double>() + eu0);
+                SB2_LAUNCH_CHECK();
+            }
+            if (full) {
+                gather_f64_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, p->perm.as<int64_t>(), est_u,
+                                                                              p->est_it.as<double>());
+                SB2_LAUNCH_CHECK();
+            } else if (ei1 > ei0) {
+                nmf_dot_item_kernel<<<(unsigned)ceil_div(ei1 - ei0, 256), 256, 0, st>>>(
+                    ei0, ei1, f, p->i_it.as<int32_t>(), p->u_it.as<int32_t>(), pu_cur, qi_cur, p->est_it.as<double>());
+                SB2_LAUNCH_CHECK();
+            }
         }
-        SB2_TRY(nmf_pass(n_users, f, ptr_u.as<int64_t>(), i, r, est_u, pu_cur, qi_cur, pu_nxt, prm->reg_pu,
-                         status_d.as<int>(), st));
-        SB2_TRY(nmf_pass(n_items, f, ptr_i.as<int64_t>(), u_it.as<int32_t>(), r_it.as<double>(), est_i, qi_cur, pu_cur,
-                         qi_nxt, prm->reg_qi, status_d.as<int>(), st));
-        std::swap(pu_cur, pu_nxt);
-        std::swap(qi_cur, qi_nxt);
     }
-    if (pu_cur != pu) {
-        SB2_CUDA(cudaMemcpyAsync(pu, pu_cur, (size_t)n_users * f * 8, cudaMemcpyDeviceToDevice, st));
-        SB2_CUDA(cudaMemcpyAsync(qi, qi_cur, (size_t)n_items * f * 8, cudaMemcpyDeviceToDevice, st));
-    }
+    // segment ranges: shift the CSR offsets / row pointers so that segment 0 of the launch is u0 (i0)
+    SB2_TRY(nmf_pass(u1 - u0, f, p->ptr_u.as<int64_t>() + u0, p->i, p->r, est_u, pu_cur + (size_t)u0 * f, qi_cur,
+                     pu_new + (size_t)u0 * f, prm->reg_pu, p->status.as<int>(), st));
+    SB2_TRY(nmf_pass(i1 - i0, f, p->ptr_i.as<int64_t>() + i0, p->u_it.as<int32_t>(), p->r_it.as<double>(),
+                     p->est_it.as<double>(), qi_cur + (size_t)i0 * f, pu_cur, qi_new + (size_t)i0 * f, prm->reg_qi,
+                     p->status.as<int>(), st));
+    return SB2_OK;
+}
+
+// synchronises the stream; SB2_ERR_ZERO_DIVISION where the reference raises (:723, :730)
+int nmf_plan_status(sb2_nmf_plan* p, cudaStream_t st) {
     int h[2] = {0, 0};
-    SB2_CUDA(cudaMemcpyAsync(h, status_d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaMemcpyAsync(h, p->status.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     SB2_CUDA(cudaStreamSynchronize(st));
     if (h[1]) {
-        set_error("nmf_fit: (u, i, r) must be grouped by ascending u (all_ratings() order)");
+        set_error("nmf: (u, i, r) must be grouped by ascending u (all_ratings() order)");
         return SB2_ERR_INVALID;
     }
     if (h[0]) {
@@ -368,6 +435,38 @@ int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, c
         return SB2_ERR_ZERO_DIVISION;
     }
     return SB2_OK;
+}
+
+void nmf_plan_destroy(sb2_nmf_plan* p) { delete p; }
+
+int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
+                const sb2_nmf_params* prm, double* pu, double* qi, double* bu, double* bi, cudaStream_t st) {
+    sb2_nmf_plan* plan = nullptr;
+    SB2_TRY(nmf_plan_create_dev(n_users, n_items, n, u, i, r, prm->n_factors, st, &plan));
+    struct Guard {
+        sb2_nmf_plan* p;
+        ~Guard() { delete p; }
+    } guard{plan};
+    const int f = prm->n_factors;
+    DevBuf pu2, qi2;
+    SB2_TRY(pu2.alloc((size_t)n_users * f * 8, st));
+    SB2_TRY(qi2.alloc((size_t)n_items * f * 8, st));
+    SB2_CUDA(cudaMemsetAsync(bu, 0, (size_t)n_users * sizeof(double), st));
+    SB2_CUDA(cudaMemsetAsync(bi, 0, (size_t)n_items * sizeof(double), st));
+    double* pu_cur = pu;
+    double* pu_nxt = pu2.as<double>();
+    double* qi_cur = qi;
+    double* qi_nxt = qi2.as<double>();
+    for (int ep = 0; ep < prm->n_epochs; ++ep) {
+        SB2_TRY(nmf_plan_epoch_dev(plan, prm, pu_cur, qi_cur, pu_nxt, qi_nxt, bu, bi, 0, n_users, 0, n_items, st));
+        std::swap(pu_cur, pu_nxt);
+        std::swap(qi_cur, qi_nxt);
+    }
+    if (pu_cur != pu) {
+        SB2_CUDA(cudaMemcpyAsync(pu, pu_cur, (size_t)n_users * f * 8, cudaMemcpyDeviceToDevice, st));
+        SB2_CUDA(cudaMemcpyAsync(qi, qi_cur, (size_t)n_items * f * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    return nmf_plan_status(plan, st);
 }
 
 }  // namespace sb2

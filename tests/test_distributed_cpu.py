@@ -117,3 +117,10 @@ def test_sim_row_ranges_cover_and_align():
         assert rows[0][0] == 0 and rows[-1][1] == n_x
         for (lo, hi), (lo2, _) in zip(rows, rows[1:]):
             assert hi == lo2 and lo % 256 == 0 and lo <= hi
+
+
+def test_even_ranges():
+    for n, w in ((10, 3), (480000, 8), (5, 8), (17700, 4)):
+        rs = D.even_ranges(n, w)
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert max(hi - lo for lo, hi in rs) - min(hi - lo for lo, hi in rs) <= 1

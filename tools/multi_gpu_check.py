@@ -28,6 +28,23 @@ for kind in ("cosine", "pearson"):
     torch.cuda.synchronize(); out[kind + "_sharded_s"] = time.perf_counter() - t0
     ref = sims.build_device(kind, ts.n_items, yr, 1)
     out[kind + "_bit_exact"] = bool(torch.equal(full, ref))
+# NMF sharded over ranks must be bit-identical to the single-GPU fit
+import ctypes as C
+from surprise_b200 import _native as nat
+d2 = synth.ratings(30000, 4000, 2_000_000, seed=3, holdout=0.0)
+u2, i2, r2 = d2["train"]
+ts2 = sb.Trainset.from_coo(u2, i2, r2, d2["n_users"], d2["n_items"])
+uu, ii, rr = ts2.coo()
+rng = np.random.RandomState(0)
+pu0 = rng.uniform(0, 1, (ts2.n_users, 15)); qi0 = rng.uniform(0, 1, (ts2.n_items, 15))
+for biased in (0, 1):
+    prm = nat.NmfParams(n_factors=15, n_epochs=5, biased=biased, reserved=0, global_mean=float(ts2.global_mean), reg_pu=.06,
+                        reg_qi=.06, reg_bu=.02, reg_bi=.02, lr_bu=.005, lr_bi=.005)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    got = D.nmf_fit_sharded(dist if world > 1 else None, ts2.n_users, ts2.n_items, uu, ii, rr, prm, pu0, qi0)
+    torch.cuda.synchronize(); out["nmf_sharded_s_biased%d" % biased] = time.perf_counter() - t0
+    ref = D.nmf_fit_sharded(None, ts2.n_users, ts2.n_items, uu, ii, rr, prm, pu0, qi0)
+    out["nmf_bit_exact_biased%d" % biased] = bool(all(np.array_equal(a, b) for a, b in zip(got, ref)))
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
