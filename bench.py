@@ -340,6 +340,7 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    secondary = secondary_metrics(nat, ts, uu, ii, rr) if world == 1 else None
     peak, peak_src = measured_peak_gbs()
     bytes_per_update = 2 * (2 * f + 2) * 4 + 12
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else None
@@ -367,10 +368,47 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "l2": "256 MiB memset between timed steps (inside the timed region)",
                        "step": "one full fit = 20 epochs = 2e7 rating updates", "parallelism": "dsgd-ring%d" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "heldout_rmse": rmse, "wall_ms_per_step": wall_ms / args.steps}
+            "heldout_rmse": rmse, "wall_ms_per_step": wall_ms / args.steps, "secondary": secondary}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_metrics(nat, ts, uu, ii, rr):
+    """The other two quantities BASELINE.json's metric string names, on the same ml-1M-shaped ratings, outside the
+    timed region: pearson_baseline item-item similarity build (s) and NMF rating-visits/s (f=15, 50 epochs)."""
+    import torch
+    from surprise_b200 import similarities as sims
+    out = {}
+    try:
+        mu = float(ts.global_mean)
+        yr = ts.user_csr()
+        rng = np.random.RandomState(1)
+        bx, by = rng.normal(0, .3, ts.n_items), rng.normal(0, .3, ts.n_users)
+        for _ in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            sims.build_device("pearson_baseline", ts.n_items, yr, 1, mu, bx, by, 100)
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        out["pearson_baseline_sim_build_s"] = dt
+        out["sim_shape"] = "%d items x %d users, %d ratings (host CSR in, device matrix out)" % (ts.n_items, ts.n_users, len(rr))
+        f, ep = 15, 50
+        pu0 = rng.uniform(0, 1, (ts.n_users, f)); qi0 = rng.uniform(0, 1, (ts.n_items, f))
+        d = [nat.to_dev(a, t) for a, t in ((uu, np.int32), (ii, np.int32), (rr, np.float64))]
+        d_bu, d_bi = nat.empty_dev((ts.n_users,), np.float64), nat.empty_dev((ts.n_items,), np.float64)
+        prm = nat.NmfParams(n_factors=f, n_epochs=ep, biased=0, reserved=0, global_mean=0.0, reg_pu=.06, reg_qi=.06,
+                            reg_bu=.02, reg_bi=.02, lr_bu=.005, lr_bi=.005)
+        for _ in range(2):
+            d_pu, d_qi = nat.to_dev(pu0, np.float64), nat.to_dev(qi0, np.float64)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            nat.check(nat.lib().sb2_nmf_fit_dev(ts.n_users, ts.n_items, len(rr), nat.ptr(d[0]), nat.ptr(d[1]), nat.ptr(d[2]),
+                                                C.byref(prm), nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_bu), nat.ptr(d_bi),
+                                                nat.stream()))
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        out["nmf_rating_visits_per_s"] = len(rr) * ep / dt
+        out["nmf_config"] = "NMF f=15, 50 epochs, same ratings; full-shape runs: profiles/r1_configs_full_shape.json"
+    except Exception as e:  # secondary numbers must never break the headline line
+        out["error"] = repr(e)
+    return out
 
 
 def main():

@@ -40,7 +40,7 @@ struct DsgdArgs {
     int US;                             // user row stride: FP (SVD) or 3*FP (SVD++: [p | z | g], see below)
     int C;                              // CTAs per thread-block cluster (1 = no clusters); B = K * C
     int ibuf;                           // floats per item-block buffer in shared memory
-    int s_begin, s_end;                 // OUTER steps of this launch (SVD: all K = B / C; SVD++: one chunk)
+    int s_begin, s_end;                 // strata of this launch, s = T * C + t (SVD: all B; SVD++: one chunk of them)
     int rec_cap;                        // records of a cell staged in shared memory
     const int* ul;                      // records grouped by cell (stratum-major), colour-sorted inside a cell
     const int* il;
@@ -338,7 +338,11 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     // Only the K hand-offs between clusters go through L2 with the release / acquire step counters.
     const int C = a.C, K = B / C;
     const int Cl = ub / C, c = ub - Cl * C;
-    const int n_outer = a.s_end - a.s_begin;
+    // a launch covers strata [s_begin, s_end) (s = T * C + t); it may start and end in the middle of an outer step
+    // (SVD++ chunks): the first stratum of a launch always loads its block from global memory (everything was
+    // written back when the previous launch ended) and the last one always writes back.
+    const int T_begin = a.s_begin / C, T_end = (a.s_end + C - 1) / C;
+    const int n_outer = T_end - T_begin;
     int slot = 0;
     uint32_t n_push = 0;  // pushes done so far (selects the mbarrier phases)
     uint32_t left_data_bar = 0, right_free_bar = 0;  // remote addresses of ring_bar[0] (left) / ring_bar[2] (right)
@@ -348,11 +352,14 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
         right_free_bar = dsmem_addr(&ring_bar[2], (uint32_t)(c + 1 == C ? 0 : c + 1));
     }
     for (int ep = 0; ep < a.n_epochs; ++ep) {
-        for (int T = a.s_begin; T < a.s_end; ++T) {
+        for (int T = T_begin; T < T_end; ++T) {
             const int D = (Cl + T) % K;
-            const int gstep = ep * n_outer + (T - a.s_begin);
-            for (int t = 0; t < C; ++t) {
+            const int gstep = ep * n_outer + (T - T_begin);
+            const int t_lo = max(0, a.s_begin - T * C), t_hi = min(C, a.s_end - T * C);
+            for (int t = t_lo; t < t_hi; ++t) {
                 const int s = T * C + t;
+                const bool first = (t == t_lo), last = (t + 1 == t_hi);  // of this outer step within the launch
+                const bool wait_flag = first && !(ep == 0 && T == T_begin);
                 int j = c + t;
                 if (j >= C) j -= C;
                 const int ib = D * C + j;
@@ -368,14 +375,14 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
                     rr_s[x] = a.r[k0 + x];
                 }
                 for (int x = tid; x <= NW; x += nthr) wave_s[x] = a.wave_off[((size_t)s * B + ub) * (NW + 1) + x];
-                if (t == 0 && tid == 0) {
+                if (wait_flag && tid == 0) {
                     while (ld_relaxed(a.flags + ib) != gstep) { /* previous cluster still owns the super-block */ }
                     fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
                 }
                 __syncthreads();
                 const long long c1 = clock64();
                 const int ni_local = (a.n_items - ib + B - 1) / B;
-                if (SI && t == 0) {
+                if (SI && first) {
                     const int total = ni_local * F4;
                     for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
                         float4 v[4];
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
                     }
                 }
                 const long long c3 = clock64();
-                if (t + 1 < C) {
+                if (!last) {
                     // fast hop (neighbour-to-neighbour, no cluster-wide barrier): once the left neighbour has finished
                     // reading its spare buffer (its previous push), copy my block into it through distributed shared
                     // memory, tell it the data is there, tell my right neighbour that my block buffer is reusable,
@@ -600,7 +607,7 @@ __global__ void svdpp_user_refresh_kernel(int64_t n_users, int FP, const int64_t
     if (lane == 0) cnt[u] = 0.f;
 }
 
-// y_j <- y_j (1 - lr reg)^{c_j} + lr sum_{u in U_j} g_u,  c_j = sum_{u in U_j} cnt_u: what the reference's
+// y_j <- y_j d^{c_j} + lr (1 - d^{c_j}) / (c_j (1 - d)) sum_{u in U_j} g_u,  d = 1 - lr reg,  c_j = sum_{u in U_j} cnt_u: what the reference's
 // per-rating updates y_j += lr (err q / sqrt|I_u| - reg y_j) (matrix_factorization.pyx:496-498) add up
 // to over the ratings processed since the last application, with the decay applied exactly.
 __global__ void svdpp_item_apply_kernel(int64_t n_items, int FP, const int64_t* __restrict__ i_ptr,
@@ -615,11 +622,17 @@ __global__ void svdpp_item_apply_kernel(int64_t n_items, int FP, const int64_t* 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if (c == 0.f) return;
-    const float decay = expf(c * log1pf(-lr * reg));
+    // the c decays and the gradient instalments interleave in the reference; with the instalments spread
+    // evenly over the c events their decayed sum is acc / c * sum_{k<c} d^k = acc * (1 - d^c) / (c (1 - d)).
+    // For a popular item c * lr * reg >> 1 within one chunk, and the undamped sum overshoots several-fold.
+    const float lg = c * log1pf(-lr * reg);
+    const float decay = expf(lg);
+    const float x = c * lr * reg;
+    const float gain = x > 0.f ? lr * (-expm1f(lg)) / x : lr;  // reg == 0: no decay, plain sum
     for (int col = lane; col < FP; col += 32) {
         float acc = 0.f;
         for (int64_t a = b; a < e; ++a) acc += urows[(size_t)iu_idx[a] * 3 * FP + 2 * FP + col];
-        yj[(size_t)j * FP + col] = yj[(size_t)j * FP + col] * decay + lr * acc;
+        yj[(size_t)j * FP + col] = yj[(size_t)j * FP + col] * decay + gain * acc;
     }
 }
 
@@ -747,6 +760,7 @@ static void dsgd_launch_config(const sb2_svd_plan* p, int n_blocks, cudaLaunchCo
 static int dsgd_launch(const sb2_svd_plan* p, const DsgdArgs& a, cudaStream_t st) {
     dsgd_kernel_t kern = dsgd_kernel(p);
     SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p->C > 8 ? 1 : 0));
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
     dsgd_launch_config(p, p->B, &cfg, attr, st);
@@ -813,32 +827,6 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     int B = sm_count();
     int C = 1;
     const int b_rows = (int)std::min<int64_t>(std::min(n_users, n_items), 1 << 20);
-    if (const char* e = getenv("SB2_DSGD_CLUSTER")) C = atoi(e);
-    else C = 8;
-    if (C != 1 && C != 2 && C != 4 && C != 8) C = 1;
-    {
-        const int b_cells = std::max(1, (int)sqrt((double)std::max<int64_t>(n, 1) / 16.0));
-        int b_lim = std::min(std::min(B, b_rows), b_cells);
-        if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
-            const int b = atoi(e);
-            if (b > 0 && b <= sm_count()) b_lim = std::min(b, b_rows);
-        }
-        while (C > 1 && b_lim < 2 * C) C >>= 1;  // at least two clusters, else fall back to smaller clusters
-        if (C > 1) {
-            B = b_lim / C * C;
-        } else {
-            const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
-            B = std::min(std::min(sm_count(), b_rows), b_work);
-            if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
-                const int b = atoi(e);
-                if (b > 0 && b <= sm_count()) B = std::min(b, b_rows);
-            }
-        }
-    }
-    if (B < 1) B = 1;
-    p->B = B;
-    p->C = C;
-    int max_ul = (int)ceil_div(n_users, B), max_il = (int)ceil_div(n_items, B);
     const size_t budget = 200 * 1024;
     auto plan_smem = [&](int Bc, int Cc, bool* st_i, bool* st_u, size_t* used, int* ibuf) {
         const int mul = (int)ceil_div(n_users, Bc), mil = (int)ceil_div(n_items, Bc);
@@ -852,37 +840,60 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         *used = fixed + (*st_i ? need_i : 0) + (*st_u ? need_u : 0);
     };
     size_t smem_used = 0;
-    plan_smem(B, C, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
-    if (C > 1) {
-        // clusters need the item block in shared memory (twice) and enough co-resident clusters
-        bool ok = p->stage_i;
-        if (ok) {
-            p->smem = smem_used + 256 * 12 + 64;
-            dsgd_kernel_t kern = dsgd_kernel(p);
-            int max_clusters = 0;
-            cudaLaunchConfig_t cfg;
-            cudaLaunchAttribute attr[2];
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 16 * 1024));
-            dsgd_launch_config(p, B, &cfg, attr, st);
-            cfg.dynamicSmemBytes = budget;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kern, &cfg) != cudaSuccess) {
-                cudaGetLastError();
-                max_clusters = 0;
-            }
-            if (max_clusters < 2) ok = false;
-            else if (B / C > max_clusters) B = max_clusters * C;
+    int b_lim;
+    {
+        const int b_cells = std::max(1, (int)sqrt((double)std::max<int64_t>(n, 1) / 16.0));
+        b_lim = std::min(std::min(B, b_rows), b_cells);
+        if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
+            const int b = atoi(e);
+            if (b > 0 && b <= sm_count()) b_lim = std::min(b, b_rows);
         }
-        if (!ok) {
-            C = 1;
-            const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
-            B = std::min(std::min(sm_count(), b_rows), b_work);
-        }
-        p->B = B;
-        p->C = C;
-        max_ul = (int)ceil_div(n_users, B);
-        max_il = (int)ceil_div(n_items, B);
-        plan_smem(B, C, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
     }
+    // largest cluster size (16 is the non-portable maximum, 7 such clusters are co-resident on a B200) that
+    // leaves at least two clusters, fits two item buffers in shared memory and passes the occupancy query
+    int c_first = 16;
+    if (const char* e = getenv("SB2_DSGD_CLUSTER")) c_first = atoi(e);
+    bool clustered = false;
+    for (int Cc = 16; Cc >= 2 && !clustered; Cc >>= 1) {
+        if (Cc > c_first || b_lim < 2 * Cc) continue;
+        int Bc = b_lim / Cc * Cc;
+        p->B = Bc; p->C = Cc;
+        plan_smem(Bc, Cc, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
+        if (!p->stage_i) continue;
+        p->smem = smem_used + 256 * 12 + 64;
+        dsgd_kernel_t kern = dsgd_kernel(p);
+        int max_clusters = 0;
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[2];
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 16 * 1024));
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, Cc > 8 ? 1 : 0);
+        dsgd_launch_config(p, Bc, &cfg, attr, st);
+        cfg.dynamicSmemBytes = budget;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kern, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            max_clusters = 0;
+        }
+        if (max_clusters < 2) continue;
+        if (Bc / Cc > max_clusters) Bc = max_clusters * Cc;
+        B = Bc;
+        C = Cc;
+        clustered = true;
+    }
+    if (!clustered) {
+        // no clusters: every hop is an L2 hop (~8k cycles) and bigger cells win: B ~ sqrt(N / (10 W))
+        C = 1;
+        const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
+        B = std::min(std::min(sm_count(), b_rows), b_work);
+        if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
+            const int b = atoi(e);
+            if (b > 0 && b <= sm_count()) B = std::min(b, b_rows);
+        }
+    }
+    if (B < 1) B = 1;
+    p->B = B;
+    p->C = C;
+    int max_ul = (int)ceil_div(n_users, B), max_il = (int)ceil_div(n_items, B);
+    plan_smem(B, C, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
     const size_t n_cells = (size_t)B * B;
 
     auto fail = [&](int rc) { plan_free(p); return rc; };
@@ -1034,10 +1045,10 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         cleanup2();
         // y_j is applied `chunks` times per epoch: a popular item must not receive more than ~32 raters'
         // accumulated gradients in one step (tools/proto/svdpp_variants.py, DESIGN.md "SVD++")
-        p->chunks = std::max(1, std::min(B / C, (int)ceil_div(max_raters, 32)));
+        p->chunks = std::max(1, std::min(B, (int)ceil_div(max_raters, 32)));
         if (const char* e = getenv("SB2_SVDPP_CHUNKS")) {
             const int c = atoi(e);
-            if (c >= 1) p->chunks = std::min(c, B / C);
+            if (c >= 1) p->chunks = std::min(c, B);
         }
     }
     // shared-memory plan: wave table + cell offsets, item buffer(s), user block, then as many of a cell's
@@ -1084,7 +1095,6 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags;
     a.isq = p->isq; a.cnt = p->cnt;
     a.C = p->C; a.ibuf = p->ibuf;
-    const int K = p->B / p->C;
     const sb2_sgd_params& q = p->prm;
     a.mu = (q.biased || p->with_yj) ? (float)q.global_mean : 0.f;
     a.lr_bu = (float)q.lr_bu; a.lr_bi = (float)q.lr_bi; a.lr_pu = (float)q.lr_pu; a.lr_qi = (float)q.lr_qi;
@@ -1092,17 +1102,30 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     a.lr_yj = (float)q.lr_yj; a.reg_yj = (float)q.reg_yj;
     a.prof = p->prof;
     if (!p->with_yj) {
-        a.n_epochs = n_epochs; a.s_begin = 0; a.s_end = K;
-        SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
-        return dsgd_launch(p, a, st);
+        int split = 1;  // SB2_DSGD_SPLIT=n: every epoch as n launches over strata ranges (same updates, same order)
+        if (const char* e = getenv("SB2_DSGD_SPLIT")) split = std::max(1, std::min(atoi(e), p->B));
+        if (split == 1) {
+            a.n_epochs = n_epochs; a.s_begin = 0; a.s_end = p->B;
+            SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+            return dsgd_launch(p, a, st);
+        }
+        for (int ep = 0; ep < n_epochs; ++ep)
+            for (int c = 0; c < split; ++c) {
+                a.n_epochs = 1;
+                a.s_begin = (int)((int64_t)p->B * c / split);
+                a.s_end = (int)((int64_t)p->B * (c + 1) / split);
+                SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+                SB2_TRY(dsgd_launch(p, a, st));
+            }
+        return SB2_OK;
     }
     // SVD++: per epoch `chunks` x { refresh z_u and clear g_u; strata of the chunk; apply g to y_j }
     const unsigned ub = (unsigned)ceil_div(p->n_users * 32, 256), ib = (unsigned)ceil_div(p->n_items * 32, 256);
     for (int ep = 0; ep < n_epochs; ++ep)
         for (int c = 0; c < p->chunks; ++c) {
             a.n_epochs = 1;
-            a.s_begin = (int)((int64_t)K * c / p->chunks);
-            a.s_end = (int)((int64_t)K * (c + 1) / p->chunks);
+            a.s_begin = (int)((int64_t)p->B * c / p->chunks);
+            a.s_end = (int)((int64_t)p->B * (c + 1) / p->chunks);
             if (a.s_begin == a.s_end) continue;
             svdpp_user_refresh_kernel<<<ub, 256, 0, st>>>(p->n_users, p->FP, p->u_ptr, p->ui_idx, p->yj, p->isq, p->pu,
                                                           p->cnt);

@@ -427,6 +427,22 @@ def test_svd_conflict_free_input_matches_oracle():
         assert np.allclose(algo.bu, bu, rtol=0, atol=2e-6) and np.allclose(algo.bi, bi, rtol=0, atol=2e-6)
 
 
+def test_svd_split_launches_bit_identical(monkeypatch):
+    """A launch may cover any range of strata (the SVD++ path applies y_j between ranges): running every epoch
+    as n launches performs the same updates in the same order, so the factors must not change by one bit --
+    this pins the hand-over of item blocks across launch boundaries (cluster ring + L2 mailboxes)."""
+    d = synth.ratings(3000, 1500, 200_000, seed=3)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    monkeypatch.delenv("SB2_DSGD_SPLIT", raising=False)
+    base = sb.SVD(n_factors=24, n_epochs=3, random_state=2).fit(ts)
+    for split in (2, 3, 7, 16, 10_000):
+        monkeypatch.setenv("SB2_DSGD_SPLIT", str(split))
+        algo = sb.SVD(n_factors=24, n_epochs=3, random_state=2).fit(ts)
+        for name in ("pu", "qi", "bu", "bi"):
+            assert np.array_equal(getattr(algo, name), getattr(base, name)), (split, name)
+
+
 def test_u1_svdpp_rmse(u1, u1_golden):
     ts, testset = u1
     algo = sb.SVDpp(random_state=0).fit(ts)

@@ -13,7 +13,7 @@ def rmse(pu, qi, yj, bu, bi, mu, ptr, idx, tu, ti, tr):
     return float(np.sqrt(np.mean((np.clip(est, 1, 5) - tr) ** 2)))
 
 
-def variant_A(u, i, r, ptr, idx, pu, qi, yj, n_epochs, mu, lr, reg, order_seed=None, chunks=1):
+def variant_A(u, i, r, ptr, idx, pu, qi, yj, n_epochs, mu, lr, reg, order_seed=None, chunks=1, expint=False):
     """per-epoch: z_u from y; pass over ratings with own-effect z update and per-user gradient accumulation;
     y applied item-side in `chunks` instalments per epoch."""
     nu, f = pu.shape; ni = qi.shape[0]
@@ -40,8 +40,13 @@ def variant_A(u, i, r, ptr, idx, pu, qi, yj, n_epochs, mu, lr, reg, order_seed=N
             # item side: decay by the number of (rating of u) events seen by each y_j, then add the gradients
             cj = np.zeros(ni); np.add.at(cj, idx, cnt[users_of_rating])
             gj = np.zeros((ni, f)); np.add.at(gj, idx, g[users_of_rating])
-            yj *= ((1 - lr * reg) ** cj)[:, None]
-            yj += lr * gj
+            dec = (1 - lr * reg) ** cj
+            yj *= dec[:, None]
+            if expint:  # gradients spread uniformly over the c_j decays: sum_k d^k = (1 - d^c) / (1 - d)
+                fac = np.where(cj > 0, (1 - dec) / np.maximum(cj * lr * reg, 1e-300), 1.0)
+                yj += lr * gj * fac[:, None]
+            else:
+                yj += lr * gj
             if c + 1 < chunks:
                 z = np.zeros((nu, f)); np.add.at(z, users_of_rating, yj[idx]); z /= sq[:, None]
     return pu, qi, yj, bu, bi
@@ -64,7 +69,10 @@ def run(name, u, i, r, nu, ni, tu, ti, tr, f=20, n_epochs=20):
         for seed in (None, 1):
             pu, qi, yj = init()
             a = variant_A(uu, ii, rr, ptr, idx, pu, qi, yj, n_epochs, mu, .007, .02, seed, chunks)
-            print(name, "  A chunks=%2d order=%s rmse %.5f" % (chunks, "file" if seed is None else "perm", rmse(*a[:3], a[3], a[4], mu, ptr, idx, tu, ti, tr)))
+            print(name, "  A chunks=%2d order=%s rmse %.5f" % (chunks, "file" if seed is None else "perm", rmse(*a[:3], a[3], a[4], mu, ptr, idx, tu, ti, tr)), flush=True)
+        pu, qi, yj = init()
+        a = variant_A(uu, ii, rr, ptr, idx, pu, qi, yj, n_epochs, mu, .007, .02, 1, chunks, True)
+        print(name, "  A chunks=%2d order=perm EXPINT rmse %.5f" % (chunks, rmse(*a[:3], a[3], a[4], mu, ptr, idx, tu, ti, tr)), flush=True)
 
 
 if __name__ == "__main__":
@@ -74,9 +82,10 @@ if __name__ == "__main__":
     data = sb.Dataset.load_from_folds([(os.path.join(G, "u1_ml100k_train"), os.path.join(G, "u1_ml100k_test"))], sb.Reader("ml-100k"))
     ts, te = next(PredefinedKFold().split(data))
     u, i, r = ts.coo(); iu, ii = inner_pairs(ts, te); tr = np.array([t[2] for t in te])
-    run("u1", u, i, r, ts.n_users, ts.n_items, iu, ii, tr)
-    d = synth.ratings(600, 400, 30000, seed=2)
-    run("synth", *d["train"], d["n_users"], d["n_items"], *d["test"], n_epochs=10)
+    if "dense" not in sys.argv:
+        run("u1", u, i, r, ts.n_users, ts.n_items, iu, ii, tr)
+        d = synth.ratings(600, 400, 30000, seed=2)
+        run("synth", *d["train"], d["n_users"], d["n_items"], *d["test"], n_epochs=10)
     if len(sys.argv) > 1 and sys.argv[1] == "dense":
         d = synth.ratings(3000, 300, 200000, seed=5)
         run("dense", *d["train"], d["n_users"], d["n_items"], *d["test"], n_epochs=10)
