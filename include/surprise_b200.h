@@ -244,6 +244,25 @@ int sb2_knn_predict(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
                     int min_k, int mode, double global_mean, const double* bx, const double* by, double* est,
                     int32_t* actual_k, uint8_t* impossible);
 
+/* ------------------------------------------------------------------------------------------------
+ * SlopeOne ("next" row 4 of the hot-path table).  sb2_slope_one_fit replaces the two loops of
+ * SlopeOne.fit (prediction_algorithms/slope_one.pyx:59-70): freq[i][j] = number of users who rated both
+ * items (n_items x n_items int64; diagonal = raters of i), dev[i][j] = mean over those users of
+ * r_ui - r_uj with the ratings TRUNCATED to C ints exactly as the reference's `cdef int r_ui, r_uj` does
+ * (slope_one.pyx:52); 0 / 0 = NaN where freq is 0; dev[j][i] = -dev[i][j]; dev[i][i] = 0.  Both are
+ * by-products of the similarity contractions (freq = M M^T, sum r_ui = R M^T) on the tensor cores and are
+ * bit-identical to the reference.  u_ptr / i_idx / r: the ur CSR (trainset.ur flattened, user-major).
+ * sb2_slope_one_predict replaces SlopeOne.estimate (:82-97); user_mean[u] is computed by the host mirror.
+ * impossible[k] = 1 where the reference raises PredictionImpossible (u[k] < 0 or i[k] < 0).
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx,
+                          const double* r, int64_t nnz, int64_t* freq_out, double* dev_out, void* stream);
+int sb2_slope_one_fit(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx,
+                      const double* r, int64_t* freq_out, double* dev_out);
+int sb2_slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t n_items,
+                              const int64_t* freq, const double* dev, const int64_t* u_ptr, const int32_t* i_idx,
+                              const double* user_mean, double* est, uint8_t* impossible, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

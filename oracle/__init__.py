@@ -233,6 +233,31 @@ def knn_estimate(x, y, sim, y_ptr, x_idx, r, k, min_k, baseline=0, global_mean=0
     return est, ak, imp
 
 
+def slope_one_fit(n_items, u_ptr, i_idx, r):
+    u_ptr, i_idx, r = _i64(u_ptr), _i32(i_idx), _f64(r)
+    freq = np.empty((n_items, n_items), dtype=np.int64)
+    dev = np.empty((n_items, n_items), dtype=np.float64)
+    rc = lib().orc_slope_one_fit(C.c_int64(n_items), C.c_int64(len(u_ptr) - 1), _p(u_ptr, C.c_int64),
+                                 _p(i_idx, C.c_int32), _p(r, C.c_double), _p(freq, C.c_int64), _p(dev, C.c_double))
+    _check(rc)
+    return freq, dev
+
+
+def slope_one_estimate(u, i, freq, dev, u_ptr, i_idx, user_mean):
+    u, i = _i32(u), _i32(i)
+    freq = np.ascontiguousarray(freq, dtype=np.int64)
+    dev, user_mean = _f64(dev), _f64(user_mean)
+    u_ptr, i_idx = _i64(u_ptr), _i32(i_idx)
+    est = np.empty(len(u))
+    imp = np.empty(len(u), dtype=np.uint8)
+    rc = lib().orc_slope_one_estimate(C.c_int64(len(u)), _p(u, C.c_int32), _p(i, C.c_int32),
+                                      C.c_int64(freq.shape[0]), _p(freq, C.c_int64), _p(dev, C.c_double),
+                                      _p(u_ptr, C.c_int64), _p(i_idx, C.c_int32), _p(user_mean, C.c_double),
+                                      _p(est, C.c_double), _p(imp, C.c_uint8))
+    _check(rc)
+    return est, imp
+
+
 def reference_path():
     """Directory holding the compiled reference package (oracle/_ref), or None."""
     p = os.path.join(_HERE, "_ref")

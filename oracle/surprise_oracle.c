@@ -516,3 +516,60 @@ int orc_knn_estimate(int64_t n_pairs, const int32_t *x, const int32_t *y, int64_
     free(buf);
     return ORC_OK;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SlopeOne.fit (prediction_algorithms/slope_one.pyx:44-80).  u_ptr / i_idx / r: trainset.ur flattened.
+ * `cdef int ... r_ui, r_uj` (:52): the ratings are converted to C ints (truncation) before the
+ * subtraction; dev accumulates the int difference as a double, is divided by freq for i < j
+ * (0 / 0 -> NaN, no exception: the module is compiled with cdivision semantics for this statement)
+ * and mirrored with a sign flip; dev[i][i] = 0.  freq is int64 and keeps its diagonal.
+ * ------------------------------------------------------------------------------------------ */
+int orc_slope_one_fit(int64_t n_items, int64_t n_users, const int64_t *u_ptr, const int32_t *i_idx,
+                      const double *r, int64_t *freq, double *dev)
+{
+    const size_t nn = (size_t)n_items * (size_t)n_items;
+    memset(freq, 0, nn * sizeof(int64_t));
+    for (size_t k = 0; k < nn; ++k) dev[k] = 0.0;
+    for (int64_t u = 0; u < n_users; ++u)
+        for (int64_t a = u_ptr[u]; a < u_ptr[u + 1]; ++a) {
+            const int r_ui = (int)r[a];
+            for (int64_t b = u_ptr[u]; b < u_ptr[u + 1]; ++b) {
+                const int r_uj = (int)r[b];
+                const size_t o = (size_t)i_idx[a] * (size_t)n_items + (size_t)i_idx[b];
+                freq[o] += 1;
+                dev[o] += r_ui - r_uj;
+            }
+        }
+    for (int64_t i = 0; i < n_items; ++i) {
+        dev[(size_t)i * n_items + i] = 0;
+        for (int64_t j = i + 1; j < n_items; ++j) {
+            const size_t o = (size_t)i * n_items + j;
+            dev[o] /= (double)freq[o];
+            dev[(size_t)j * n_items + i] = -dev[o];
+        }
+    }
+    return ORC_OK;
+}
+
+/* SlopeOne.estimate (slope_one.pyx:82-97): Ri = items j of ur[u] with freq[i, j] > 0;
+ * est = user_mean[u] + sum(dev[i, j] for j in Ri) / len(Ri), sum() left to right from 0. */
+int orc_slope_one_estimate(int64_t n_pairs, const int32_t *u, const int32_t *i, int64_t n_items,
+                           const int64_t *freq, const double *dev, const int64_t *u_ptr,
+                           const int32_t *i_idx, const double *user_mean, double *est,
+                           uint8_t *impossible)
+{
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        impossible[p] = 0;
+        if (u[p] < 0 || i[p] < 0) { impossible[p] = 1; est[p] = 0.0; continue; }
+        double sum = 0.0;
+        int64_t cnt = 0;
+        for (int64_t a = u_ptr[u[p]]; a < u_ptr[u[p] + 1]; ++a) {
+            const size_t o = (size_t)i[p] * (size_t)n_items + (size_t)i_idx[a];
+            if (freq[o] > 0) { sum += dev[o]; ++cnt; }
+        }
+        double e = user_mean[u[p]];
+        if (cnt) e += sum / (double)cnt;
+        est[p] = e;
+    }
+    return ORC_OK;
+}

@@ -8,10 +8,10 @@ of libsurprise_b200.so (include/surprise_b200.h).  There is no CPU fallback.
 from . import accuracy, dump, similarities
 from .dataset import Dataset
 from .prediction_algorithms import (AlgoBase, BaselineOnly, KNNBaseline, KNNBasic, KNNWithMeans, KNNWithZScore, NMF,
-                                    SVD, SVDpp, Prediction, PredictionImpossible)
+                                    SVD, SVDpp, SlopeOne, Prediction, PredictionImpossible)
 from .reader import Reader
 from .trainset import Trainset
 
-__all__ = ["AlgoBase", "BaselineOnly", "KNNBasic", "KNNBaseline", "KNNWithMeans", "KNNWithZScore", "SVD", "SVDpp", "NMF", "Prediction",
+__all__ = ["AlgoBase", "BaselineOnly", "KNNBasic", "KNNBaseline", "KNNWithMeans", "KNNWithZScore", "SVD", "SVDpp", "NMF", "SlopeOne", "Prediction",
            "PredictionImpossible", "Dataset", "Reader", "Trainset", "accuracy", "dump", "similarities"]
 __version__ = "0.1.0"

@@ -79,6 +79,9 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp]),
     "sb2_knn_predict": (_int, [_i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _int, _dbl, _vp, _vp, _vp,
                                _vp, _vp]),
+    "sb2_slope_one_fit_dev": (_int, [_i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "sb2_slope_one_fit": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "sb2_slope_one_predict_dev": (_int, [_i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

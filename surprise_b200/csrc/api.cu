@@ -61,6 +61,11 @@ int knn_predict_dev(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
                     int64_t sim_ld, const int64_t* y_ptr, const int32_t* x_idx, const double* r, int k, int min_k,
                     int mode, double mu, const double* bx, const double* by, double* est, int32_t* actual_k,
                     uint8_t* impossible, cudaStream_t st);
+int slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx, const double* r,
+                      int64_t nnz, int64_t* freq_out, double* dev_out, cudaStream_t st);
+int slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t n_items, const int64_t* freq,
+                          const double* dev, const int64_t* u_ptr, const int32_t* i_idx, const double* user_mean,
+                          double* est, uint8_t* impossible, cudaStream_t st);
 int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
                         const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
                         const int32_t* ui_idx, cudaStream_t st, sb2_svd_plan** out);
@@ -551,6 +556,40 @@ int sb2_knn_predict(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
     SB2_TRY(download(impossible, d_imp.p, (size_t)n_pairs, st));
     SB2_CUDA(cudaStreamSynchronize(st));
     return SB2_OK;
+}
+
+int sb2_slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx, const double* r,
+                          int64_t nnz, int64_t* freq_out, double* dev_out, void* stream) {
+    SB2_TRY(ensure_device());
+    return slope_one_fit_dev(n_items, n_users, u_ptr, i_idx, r, nnz, freq_out, dev_out, (cudaStream_t)stream);
+}
+
+int sb2_slope_one_fit(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx, const double* r,
+                      int64_t* freq_out, double* dev_out) {
+    SB2_TRY(ensure_device());
+    cudaStream_t st = nullptr;
+    const int64_t nnz = u_ptr[n_users];
+    const size_t nn = (size_t)n_items * (size_t)n_items;
+    DevBuf d_ptr, d_idx, d_r, d_freq, d_dev;
+    SB2_TRY(upload(d_ptr, u_ptr, (size_t)n_users + 1, st));
+    SB2_TRY(upload(d_idx, i_idx, (size_t)nnz, st));
+    SB2_TRY(upload(d_r, r, (size_t)nnz, st));
+    SB2_TRY(d_freq.alloc(nn * 8, st));
+    SB2_TRY(d_dev.alloc(nn * 8, st));
+    SB2_TRY(slope_one_fit_dev(n_items, n_users, d_ptr.as<int64_t>(), d_idx.as<int32_t>(), d_r.as<double>(), nnz,
+                              d_freq.as<int64_t>(), d_dev.as<double>(), st));
+    SB2_TRY(download(freq_out, d_freq.p, nn, st));
+    SB2_TRY(download(dev_out, d_dev.p, nn, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    return SB2_OK;
+}
+
+int sb2_slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t n_items, const int64_t* freq,
+                              const double* dev, const int64_t* u_ptr, const int32_t* i_idx, const double* user_mean,
+                              double* est, uint8_t* impossible, void* stream) {
+    SB2_TRY(ensure_device());
+    return slope_one_predict_dev(n_pairs, u, i, n_items, freq, dev, u_ptr, i_idx, user_mean, est, impossible,
+                                 (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -191,4 +191,68 @@ int knn_predict_dev(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
     return SB2_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// SlopeOne.estimate (slope_one.pyx:82-97).  One warp per (u, i):
+//   Ri = [j for (j, _) in ur[u] if freq[i, j] > 0];  est = user_mean[u] + sum(dev[i, j] for j in Ri) / len(Ri)
+// Python's sum() adds left to right in ur[u] order; lanes gather 32 entries of row i at a time and the
+// warp folds them in lane order (every lane performs the same additions), so the bits match.
+// ------------------------------------------------------------------------------------------------
+__global__ void slope_one_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ u, const int32_t* __restrict__ i,
+                                         int64_t n_items, const int64_t* __restrict__ freq,
+                                         const double* __restrict__ dev, const int64_t* __restrict__ u_ptr,
+                                         const int32_t* __restrict__ i_idx, const double* __restrict__ user_mean,
+                                         double* __restrict__ est, uint8_t* __restrict__ impossible) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; p < n_pairs; p += nwarps) {
+        const int32_t uu = u[p], ii = i[p];
+        double e = 0.0;
+        uint8_t imp = 0;
+        if (uu < 0 || ii < 0) {
+            imp = 1;  // PredictionImpossible('User and/or item is unkown.')
+        } else {
+            const int64_t b = u_ptr[uu], len = u_ptr[uu + 1] - b;
+            const int64_t* frow = freq + (size_t)ii * (size_t)n_items;
+            const double* drow = dev + (size_t)ii * (size_t)n_items;
+            double sum = 0.0;
+            int64_t cnt = 0;
+            for (int64_t a0 = 0; a0 < len; a0 += 32) {
+                const int64_t a = a0 + lane;
+                bool rel = false;
+                double d = 0.0;
+                if (a < len) {
+                    const int32_t j = i_idx[b + a];
+                    rel = frow[j] > 0;
+                    if (rel) d = drow[j];
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, rel);
+                cnt += __popc(m);
+                for (unsigned rest = m; rest; rest &= rest - 1) {
+                    const int src = __ffs(rest) - 1;
+                    sum = __dadd_rn(sum, __shfl_sync(0xFFFFFFFFu, d, src));
+                }
+            }
+            e = user_mean[uu];
+            if (cnt > 0) e = __dadd_rn(e, __ddiv_rn(sum, (double)cnt));
+        }
+        if (lane == 0) {
+            est[p] = e;
+            impossible[p] = imp;
+        }
+    }
+}
+
+int slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t n_items, const int64_t* freq,
+                          const double* dev, const int64_t* u_ptr, const int32_t* i_idx, const double* user_mean,
+                          double* est, uint8_t* impossible, cudaStream_t st) {
+    if (n_pairs <= 0) return SB2_OK;
+    int64_t blocks = ceil_div(n_pairs * 32, 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    slope_one_predict_kernel<<<(unsigned)blocks, 256, 0, st>>>(n_pairs, u, i, n_items, freq, dev, u_ptr, i_idx, user_mean,
+                                                              est, impossible);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
 }  // namespace sb2

@@ -35,14 +35,15 @@ __device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ ptr,
 }
 
 // pass 1: check the ratings are integer multiples of 1/denom and find max q; a_y range for baselines
-__global__ void sim_analyze_kernel(const double* __restrict__ r, int64_t nnz, double denom, int* __restrict__ status,
+__global__ void sim_analyze_kernel(const double* __restrict__ r, int64_t nnz, double denom, int truncate,
+                                   int* __restrict__ status,
                                    const double* __restrict__ y_biases, int64_t n_y, double global_mean,
                                    double* __restrict__ a_y, unsigned long long* __restrict__ a_minmax) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t < nnz) {
         const double q = r[t] * denom;
-        const double qr = rint(q);
-        if (!(fabs(q - qr) <= 1e-9 * fmax(1.0, fabs(q))) || qr < 0.0 || qr > 65535.0)
+        const double qr = truncate ? trunc(q) : rint(q);  // SlopeOne reads ratings into C ints (slope_one.pyx:52)
+        if ((!truncate && !(fabs(q - qr) <= 1e-9 * fmax(1.0, fabs(q)))) || !(qr >= 0.0) || qr > 65535.0)
             atomicExch(&status[ST_BAD_RATING], 1);
         else
             atomicMax(&status[ST_MAX_Q], (int)qr);
@@ -78,6 +79,7 @@ struct PackArgs {
     int na, nc;
     int* status;
     int64_t n_x;
+    int truncate;
 };
 
 // pass 2: scatter the yr CSR into the dense K-major u8 panels
@@ -99,7 +101,7 @@ __global__ void sim_pack_kernel(const PackArgs p) {
         atomicExch(&p.status[ST_DUP], 1);
         return;
     }
-    const unsigned q = (unsigned)rint(p.r[t] * p.denom);
+    const unsigned q = (unsigned)(p.truncate ? trunc(p.r[t]) : rint(p.r[t] * p.denom));
     for (int d = 0; d < p.nq; ++d) p.q_panel[d][o] = (uint8_t)((q >> (8 * d)) & 0xFF);
     const unsigned long long s = (unsigned long long)q * q;
     for (int d = 0; d < p.ns; ++d) p.s_panel[d][o] = (uint8_t)((s >> (8 * d)) & 0xFF);
@@ -229,6 +231,40 @@ __global__ void sim_finalize_rows_kernel(const FinArgs f) {
     f.sim[(size_t)(i - f.row_begin) * f.n_x + j] = s;
 }
 
+// SlopeOne (slope_one.pyx:59-70): freq[i][j] = |U_ij| (int64, symmetric, diagonal = raters of i);
+// dev[i][j] = (sum_{u in U_ij} r_ui - r_uj) / freq[i][j] for i < j (0 / 0 = NaN where no common user),
+// dev[j][i] = -dev[i][j], dev[i][i] = 0.  The sums are integers (ratings truncated to C ints), so
+// si - sj below is the reference's accumulated value exactly.  Same 32x32 tile walk as the symmetric
+// similarity finalize.
+__global__ void slope_finalize_kernel(const FinArgs f, int64_t* __restrict__ freq_out, double* __restrict__ dev_out) {
+    __shared__ double tdev[32][33];
+    __shared__ double tfreq[32][33];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;
+    const int tx = threadIdx.x, ty0 = threadIdx.y;
+    for (int ty = ty0; ty < 32; ty += 8) {
+        const int64_t i = (int64_t)ti * 32 + ty, j = (int64_t)tj * 32 + tx;
+        double d = 0.0, n = 0.0;
+        if (i < f.n_x && j < f.n_x && i <= j) {
+            const size_t o = (size_t)i * f.ld + j;
+            n = f.freq[o];
+            if (i < j) d = __ddiv_rn(__dsub_rn(f.si[o], f.sj[o]), n);
+            freq_out[(size_t)i * f.n_x + j] = (int64_t)n;
+            dev_out[(size_t)i * f.n_x + j] = d;
+        }
+        tdev[ty][tx] = d;
+        tfreq[ty][tx] = n;
+    }
+    __syncthreads();
+    for (int ty = ty0; ty < 32; ty += 8) {
+        const int64_t i = (int64_t)tj * 32 + ty, j = (int64_t)ti * 32 + tx;
+        if (i < f.n_x && j < f.n_x && j < i) {
+            freq_out[(size_t)i * f.n_x + j] = (int64_t)tfreq[tx][ty];
+            dev_out[(size_t)i * f.n_x + j] = -tdev[tx][ty];
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // driver
 // ----------------------------------------------------------------------------------------------
@@ -238,11 +274,14 @@ static int n_digits(unsigned long long v) {
     return d;
 }
 
-int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
-                  int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
-                  const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
-                  cudaStream_t st) {
-    if (kind < 0 || kind > 3 || n_x <= 0 || n_y < 0 || nnz < 0 || rating_denom <= 0 || row_begin < 0 ||
+constexpr int KIND_SLOPE_ONE = 4;  // internal: freq + dev of SlopeOne from the FREQ / SI / SJ planes
+
+static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
+                    int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
+                    const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
+                    int64_t* freq_out, cudaStream_t st) {
+    const bool slope = (kind == KIND_SLOPE_ONE);
+    if (kind < 0 || kind > 4 || n_x <= 0 || n_y < 0 || nnz < 0 || rating_denom <= 0 || row_begin < 0 ||
         row_end > n_x || row_begin >= row_end) {
         set_error("sim_build: invalid argument");
         return SB2_ERR_INVALID;
@@ -276,7 +315,7 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
         const int64_t work = std::max(nnz, pb ? n_y : (int64_t)0);
         if (work > 0) {
             sim_analyze_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, st>>>(
-                r, nnz, (double)rating_denom, status_d.as<int>(), pb ? y_biases : nullptr, n_y, global_mean,
+                r, nnz, (double)rating_denom, slope ? 1 : 0, status_d.as<int>(), pb ? y_biases : nullptr, n_y, global_mean,
                 a_y_d.as<double>(), mm_d.as<unsigned long long>());
             SB2_LAUNCH_CHECK();
         }
@@ -287,12 +326,13 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
     SB2_CUDA(cudaMemcpyAsync(mm_h, mm_d.p, sizeof(mm_h), cudaMemcpyDeviceToHost, st));
     SB2_CUDA(cudaStreamSynchronize(st));
     if (status_h[ST_BAD_RATING]) {
-        set_error("sim_build: ratings are not integer multiples of 1/%d in [0, 65535/%d]", rating_denom,
-                  rating_denom);
+        if (slope) set_error("slope_one: ratings outside [0, 65535]");
+        else set_error("sim_build: ratings are not integer multiples of 1/%d in [0, 65535/%d]", rating_denom,
+                       rating_denom);
         return SB2_ERR_UNSUPPORTED;
     }
     const unsigned long long max_q = (unsigned long long)status_h[ST_MAX_Q];
-    const int nq = n_digits(max_q), ns = n_digits(max_q * max_q);
+    const int nq = n_digits(max_q), ns = slope ? 0 : n_digits(max_q * max_q);
 
     double a_shift = 0.0, a_scale = 1.0;
     int FB = 0, na = 0, nc = 0;
@@ -333,7 +373,7 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
     PackArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.y_ptr = y_ptr; pa.x_idx = x_idx; pa.r = r; pa.nnz = nnz; pa.n_y = n_y; pa.k_pad = k_pad;
-    pa.denom = (double)rating_denom; pa.n_x = n_x;
+    pa.denom = (double)rating_denom; pa.n_x = n_x; pa.truncate = slope ? 1 : 0;
     pa.m_panel = base + panel_bytes * (pi++);
     pa.nq = nq; pa.ns = ns; pa.na = na; pa.nc = nc;
     for (int d = 0; d < nq; ++d) pa.q_panel[d] = base + panel_bytes * (pi++);
@@ -366,8 +406,8 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
 
     // ---- planes + jobs ------------------------------------------------------------------------
     enum { P_FREQ, P_PRODS, P_SQI, P_SQJ, P_SI, P_SJ, P_T1IJ, P_T1JI, P_T2, P_A1, P_COUNT };
-    bool need[P_COUNT] = {true, true, true, true, false, false, false, false, false, false};
-    if (kind == SB2_SIM_PEARSON || pb) need[P_SI] = need[P_SJ] = true;
+    bool need[P_COUNT] = {true, !slope, !slope, !slope, false, false, false, false, false, false};
+    if (kind == SB2_SIM_PEARSON || pb || slope) need[P_SI] = need[P_SJ] = true;
     if (pb) need[P_T1IJ] = need[P_T1JI] = need[P_T2] = need[P_A1] = true;
     const size_t plane_elems = (size_t)rows_pad * (size_t)ld;
     int n_planes = 0;
@@ -388,7 +428,7 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
     const uint8_t* M = pa.m_panel;
     add(P_FREQ, M, M, 1.0);
     // most significant digit pair first (keeps partial sums exact and ordered by magnitude)
-    for (int s = 2 * (nq - 1); s >= 0; --s)
+    for (int s = 2 * (nq - 1); s >= 0 && need[P_PRODS]; --s)
         for (int a = nq - 1; a >= 0; --a) {
             const int b = s - a;
             if (b < 0 || b >= nq) continue;
@@ -448,7 +488,10 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
     f.inv_d = 1.0 / (double)rating_denom;
     f.inv_d2 = 1.0 / ((double)rating_denom * (double)rating_denom);
     f.min_support = min_support; f.shrinkage = shrinkage; f.sim = sim_out; f.status = status_d.as<int>();
-    if (full) {
+    if (slope) {
+        const unsigned nt = (unsigned)ceil_div(n_x, 32);
+        slope_finalize_kernel<<<dim3(nt, nt), dim3(32, 8), 0, st>>>(f, freq_out, sim_out);
+    } else if (full) {
         const unsigned nt = (unsigned)ceil_div(n_x, 32);
         sim_finalize_sym_kernel<<<dim3(nt, nt), dim3(32, 8), 0, st>>>(f);
     } else {
@@ -471,6 +514,29 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
         return SB2_ERR_ZERO_DIVISION;
     }
     return SB2_OK;
+}
+
+int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
+                  int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
+                  const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
+                  cudaStream_t st) {
+    if (kind < 0 || kind > 3) {
+        set_error("sim_build: invalid argument");
+        return SB2_ERR_INVALID;
+    }
+    return sim_core(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
+                    shrinkage, row_begin, row_end, sim_out, nullptr, st);
+}
+
+// SlopeOne.fit (slope_one.pyx:44-80): u_ptr / i_idx / r is the ur CSR (items rated by each user)
+int slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx, const double* r,
+                      int64_t nnz, int64_t* freq_out, double* dev_out, cudaStream_t st) {
+    if (!freq_out || !dev_out) {
+        set_error("slope_one_fit: null output");
+        return SB2_ERR_INVALID;
+    }
+    return sim_core(KIND_SLOPE_ONE, n_items, n_users, u_ptr, i_idx, r, nnz, 1, 0, 0.0, nullptr, nullptr, 0.0, 0, n_items,
+                    dev_out, freq_out, st);
 }
 
 }  // namespace sb2

@@ -28,9 +28,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -44,36 +41,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-        : "memory");
-}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 8 rows * 128 B
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
 // K advances inside the 128 B swizzle atom by adding the byte offset to the start address (4 MMAs of K = 32 B).
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
@@ -228,8 +203,8 @@ gemm_u8_tc_kernel(const __grid_constant__ GemmParams p, const int2* __restrict__
                         const uint32_t sb = sbase + (p.na + p.acc_b[j]) * GEMM_TILE_BYTES;
 #pragma unroll
                         for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-                            const uint64_t ad = make_desc_sw64(sa + k * GEMM_UMMA_K);
-                            const uint64_t bd = make_desc_sw64(sb + k * GEMM_UMMA_K);
+                            const uint64_t ad = make_desc_sw128(sa + k * GEMM_UMMA_K);
+                            const uint64_t bd = make_desc_sw128(sb + k * GEMM_UMMA_K);
                             tc_mma_i8_cg2(tmem_base + j * GEMM2_BN, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
                     }

@@ -17,7 +17,8 @@ What is pinned (reference file:line of the producer in parentheses):
   * u1_arrays.npz     -- sampled similarity entries, ALS/SGD baselines, NMF pu/qi (bit-exact target),
                          per-pair estimates + actual_k of the KNN algorithms, SVD/SVDpp/NMF estimates.
   * float_sims.npz    -- a 40 x 60 synthetic Jester-style FLOAT rating set: all four similarity
-                         matrices in full + KNNBaseline estimates.
+                         matrices in full + KNNBaseline estimates; SlopeOne freq / dev / estimates on it and on a
+                         30 x 25 half-star set (slope_one.pyx:44-97, incl. the C-int truncation of ratings).
 """
 import hashlib
 import json
@@ -33,7 +34,7 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 
 ref = oracle.import_reference()
-from surprise import Dataset, Reader, KNNBasic, KNNBaseline, KNNWithMeans, KNNWithZScore, SVD, SVDpp, NMF, BaselineOnly, accuracy  # noqa: E402
+from surprise import Dataset, Reader, KNNBasic, KNNBaseline, KNNWithMeans, KNNWithZScore, SVD, SVDpp, NMF, BaselineOnly, SlopeOne, accuracy  # noqa: E402
 from surprise import similarities as rsims  # noqa: E402
 from surprise.model_selection import PredefinedKFold  # noqa: E402
 
@@ -143,6 +144,11 @@ A["NMF_rs0_biased_bu"] = nmfb.bu
 nmf3, _ = run(NMF(random_state=3, n_factors=7, n_epochs=3, reg_pu=.1, reg_qi=.02), "NMF_rs3_f7_e3", keep_est=False)
 G["algos"]["NMF_rs3_f7_e3"].update(pu_sha256=sha(nmf3.pu), qi_sha256=sha(nmf3.qi))
 
+so, _ = run(SlopeOne(), "SlopeOne")
+G["slope_one"] = {"freq_sha256": sha(so.freq), "dev_nan0_sha256": sha(np.where(np.isnan(so.dev), 0.0, so.dev)),
+                  "n_nan": int(np.isnan(so.dev).sum())}
+A["SlopeOne_user_mean"] = np.array(so.user_mean)
+
 with open(os.path.join(HERE, "u1_golden.json"), "w") as fh:
     json.dump(G, fh, indent=1, sort_keys=True)
 np.savez_compressed(os.path.join(HERE, "u1_arrays.npz"), **A)
@@ -173,6 +179,23 @@ for ub in (False, True):
     preds = kb.test(tp)
     F["knnbaseline_est_" + o] = np.array([p.est for p in preds])
     F["knnbaseline_ak_" + o] = np.array([p.details.get("actual_k", -1) for p in preds], dtype=np.int32)
+# SlopeOne truncates ratings to C ints (slope_one.pyx:52): pin that on the float set and on half-stars
+so = SlopeOne().fit(ftrain)
+F["slope_freq"], F["slope_dev"], F["slope_user_mean"] = so.freq, so.dev, np.array(so.user_mean)
+preds = so.test(tp)
+F["slope_est"] = np.array([p.est for p in preds])
+rs = np.random.RandomState(9)
+hu, hi = np.nonzero(rs.rand(30, 25) < 0.4)
+hp = rs.permutation(len(hu))
+hu, hi = hu[hp].astype(np.int32), hi[hp].astype(np.int32)
+hr = rs.randint(1, 11, len(hu)) / 2.0
+htrain = Dataset.load_from_df(pd.DataFrame({"u": hu, "i": hi, "r": hr}), Reader(rating_scale=(0.5, 5))).build_full_trainset()
+so = SlopeOne().fit(htrain)
+hp_pairs = [(int(a), int(b), 0.0) for a in range(30) for b in range(0, 25, 3)]
+F["half_uid"], F["half_iid"], F["half_rating"] = hu, hi, hr
+F["half_slope_freq"], F["half_slope_dev"] = so.freq, so.dev
+F["half_slope_est"] = np.array([p.est for p in so.test(hp_pairs)])
+F["half_slope_impossible"] = np.array([p.details["was_impossible"] for p in so.test(hp_pairs)])
 F["global_mean"] = np.float64(ftrain.global_mean)
 np.savez_compressed(os.path.join(HERE, "float_sims.npz"), **F)
 print("goldens written to", HERE)

@@ -274,6 +274,70 @@ def test_u1_knn_means_zscore_end_to_end(u1, u1_golden, u1_arrays, orient):
         assert sum(p.details["was_impossible"] for p in preds) == u1_golden["algos"][tag]["n_impossible"]
 
 
+# ---- SlopeOne ("next" row 4) -----------------------------------------------------------------------------
+def _nan0(a):
+    return np.where(np.isnan(a), 0.0, a)
+
+
+def test_u1_slope_one_end_to_end(u1, u1_golden, u1_arrays):
+    """freq / dev from the tensor-core contractions and the warp-per-pair estimate: bit-identical to the
+    reference on the fixture (NaN where freq == 0, sign of NaN aside)."""
+    ts, testset = u1
+    algo = sb.SlopeOne().fit(ts)
+    g = u1_golden["slope_one"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert algo.freq.dtype == np.int64 and sha(algo.freq) == g["freq_sha256"]
+    assert sha(_nan0(algo.dev)) == g["dev_nan0_sha256"] and int(np.isnan(algo.dev).sum()) == g["n_nan"]
+    assert np.array_equal(np.array(algo.user_mean), u1_arrays["SlopeOne_user_mean"])
+    preds = algo.test(testset)
+    assert np.array_equal(np.array([p.est for p in preds]), u1_arrays["SlopeOne_est"])
+    assert repr(float(sb.accuracy.rmse(preds, verbose=False))) == u1_golden["algos"]["SlopeOne"]["rmse"]
+    assert sum(p.details["was_impossible"] for p in preds) == u1_golden["algos"]["SlopeOne"]["n_impossible"]
+    # single-pair API and pickling
+    uid, iid, _ = testset[0]
+    assert algo.predict(uid, iid).est == preds[0].est
+    clone = pickle.loads(pickle.dumps(algo))
+    assert clone.predict(uid, iid).est == preds[0].est
+
+
+def test_slope_one_truncation_and_c_abi(floats):
+    """Ratings are truncated to C ints (slope_one.pyx:52): float and half-star goldens; host-buffer C-ABI form."""
+    n_u, n_i = 40, 60
+    tp = [(int(a), int(b), 0.0) for a in range(0, n_u, 3) for b in range(0, n_i, 7)]
+    hp = [(int(a), int(b), 0.0) for a in range(30) for b in range(0, 25, 3)]
+    for uid, iid, rat, scale, pre, pairs in ((floats["uid"], floats["iid"], floats["rating"], (-10, 10), "", tp),
+                                             (floats["half_uid"], floats["half_iid"], floats["half_rating"], (0.5, 5), "half_", hp)):
+        ts = sb.Dataset.load_from_arrays(uid, iid, rat, sb.Reader(rating_scale=scale)).build_full_trainset()
+        algo = sb.SlopeOne().fit(ts)
+        assert np.array_equal(algo.freq, floats[pre + "slope_freq"])
+        assert np.array_equal(_nan0(algo.dev), _nan0(floats[pre + "slope_dev"]))
+        assert np.array_equal(np.isnan(algo.dev), np.isnan(floats[pre + "slope_dev"]))
+        preds = algo.test(pairs)
+        assert np.array_equal(np.array([p.est for p in preds]), floats[pre + "slope_est"])
+        ptr, idx, val = ts.user_csr()
+        freq = np.empty((ts.n_items, ts.n_items), dtype=np.int64); dev = np.empty((ts.n_items, ts.n_items))
+        nat.check(nat.lib().sb2_slope_one_fit(ts.n_items, ts.n_users, nat.hptr(ptr), nat.hptr(idx), nat.hptr(val),
+                                              nat.hptr(freq), nat.hptr(dev)))
+        assert np.array_equal(freq, algo.freq) and np.array_equal(dev, algo.dev, equal_nan=True)
+
+
+def test_slope_one_synthetic_vs_oracle():
+    """Half-star synthetic at a size spanning several 256-row tiles and 128-byte k-blocks, against the oracle."""
+    d = synth.ratings(1500, 700, 60_000, step=0.5, seed=8)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"], (0.5, 5.0), 0)
+    algo = sb.SlopeOne().fit(ts)
+    ptr, idx, val = ts.user_csr()
+    freq, dev = oracle.slope_one_fit(ts.n_items, ptr, idx, val)
+    assert np.array_equal(algo.freq, freq)
+    assert np.array_equal(_nan0(algo.dev), _nan0(dev)) and np.array_equal(np.isnan(algo.dev), np.isnan(dev))
+    tu, ti, _ = d["test"]
+    want, wimp = oracle.slope_one_estimate(tu, ti, freq, dev, ptr, idx, np.array(algo.user_mean))
+    got, details = algo._estimate_batch(np.asarray(tu, dtype=np.int32), np.asarray(ti, dtype=np.int32))
+    assert np.array_equal(np.array([x["was_impossible"] for x in details]), wimp > 0)
+    assert np.array_equal(got[wimp == 0], want[wimp == 0])
+
+
 def test_knn_long_lists_and_ties():
     """Lists longer than the per-warp cache and many tied similarities (stable selection order)."""
     rng = np.random.RandomState(1)

@@ -247,3 +247,40 @@ def test_float_ratings_similarities(floats):
         for kind in KINDS:
             sim = oracle.similarity(kind, n_x, ptr, idx, val, 2, float(ts.global_mean), bx, by, 100.0)
             assert np.array_equal(sim, floats["sim_%s_%s" % (kind, o)], equal_nan=True), (kind, o)
+
+
+def _nan0(a):
+    return np.where(np.isnan(a), 0.0, a)
+
+
+def test_u1_slope_one_bit_exact(u1, u1_golden, u1_arrays):
+    """SlopeOne.fit / estimate (slope_one.pyx:44-97) on the fixture: freq, dev, user means, predictions."""
+    import hashlib
+    ts, testset = u1
+    ptr, idx, val = ts.user_csr()
+    freq, dev = oracle.slope_one_fit(ts.n_items, ptr, idx, val)
+    g = u1_golden["slope_one"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(freq) == g["freq_sha256"] and sha(_nan0(dev)) == g["dev_nan0_sha256"]
+    assert int(np.isnan(dev).sum()) == g["n_nan"]
+    mean = np.array([np.mean(val[ptr[u]:ptr[u + 1]].tolist()) for u in range(ts.n_users)])
+    assert np.array_equal(mean, u1_arrays["SlopeOne_user_mean"])
+    iu, ii = inner_pairs(ts, testset)
+    est, imp = oracle.slope_one_estimate(iu, ii, freq, dev, ptr, idx, mean)
+    lo, hi = ts.rating_scale
+    assert np.array_equal(np.clip(np.where(imp > 0, ts.global_mean, est), lo, hi), u1_arrays["SlopeOne_est"])
+    assert int(imp.sum()) == u1_golden["algos"]["SlopeOne"]["n_impossible"]
+
+
+def test_slope_one_truncates_ratings(floats):
+    """`cdef int r_ui, r_uj` (slope_one.pyx:52): half-star and float ratings are truncated before differencing."""
+    import surprise_b200 as sb
+    from surprise_b200.dataset import Dataset
+    for uid, iid, rat, scale, pre in ((floats["uid"], floats["iid"], floats["rating"], (-10, 10), ""),
+                                      (floats["half_uid"], floats["half_iid"], floats["half_rating"], (0.5, 5), "half_")):
+        ts = Dataset.load_from_arrays(uid, iid, rat, sb.Reader(rating_scale=scale)).build_full_trainset()
+        ptr, idx, val = ts.user_csr()
+        freq, dev = oracle.slope_one_fit(ts.n_items, ptr, idx, val)
+        assert np.array_equal(freq, floats[pre + "slope_freq"])
+        assert np.array_equal(_nan0(dev), _nan0(floats[pre + "slope_dev"]))
+        assert np.array_equal(np.isnan(dev), np.isnan(floats[pre + "slope_dev"]))
