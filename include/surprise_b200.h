@@ -263,6 +263,15 @@ int sb2_slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* 
                               const int64_t* freq, const double* dev, const int64_t* u_ptr, const int32_t* i_idx,
                               const double* user_mean, double* est, uint8_t* impossible, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * AlgoBase.get_neighbors (algo_base.py:303-334) on the device-resident similarity matrix: for each
+ * requested row x = rows[b], the k other ids with the largest sim[x, .], in the order of the reference's
+ * stable descending sort (ties by ascending id).  out: n_rows x k int32, padded with -1 when fewer than
+ * k other ids exist (the reference returns a shorter list) or rows[b] is out of range.
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_get_neighbors_dev(int64_t n_x, const double* sim, int64_t sim_ld, int64_t n_rows, const int32_t* rows,
+                          int k, int32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

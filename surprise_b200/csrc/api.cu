@@ -61,6 +61,8 @@ int knn_predict_dev(int64_t n_pairs, const int32_t* x, const int32_t* y, int64_t
                     int64_t sim_ld, const int64_t* y_ptr, const int32_t* x_idx, const double* r, int k, int min_k,
                     int mode, double mu, const double* bx, const double* by, double* est, int32_t* actual_k,
                     uint8_t* impossible, cudaStream_t st);
+int get_neighbors_dev(int64_t n_x, const double* sim, int64_t sim_ld, int64_t n_rows, const int32_t* rows, int k,
+                      int32_t* out, cudaStream_t st);
 int slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, const int32_t* i_idx, const double* r,
                       int64_t nnz, int64_t* freq_out, double* dev_out, cudaStream_t st);
 int slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int64_t n_items, const int64_t* freq,
@@ -590,6 +592,12 @@ int sb2_slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* 
     SB2_TRY(ensure_device());
     return slope_one_predict_dev(n_pairs, u, i, n_items, freq, dev, u_ptr, i_idx, user_mean, est, impossible,
                                  (cudaStream_t)stream);
+}
+
+int sb2_get_neighbors_dev(int64_t n_x, const double* sim, int64_t sim_ld, int64_t n_rows, const int32_t* rows, int k,
+                          int32_t* out, void* stream) {
+    SB2_TRY(ensure_device());
+    return get_neighbors_dev(n_x, sim, sim_ld, n_rows, rows, k, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

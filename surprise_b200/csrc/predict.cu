@@ -255,4 +255,79 @@ int slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, i
     return SB2_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// AlgoBase.get_neighbors (algo_base.py:303-334): others = [(x, sim[iid, x]) for x != iid];
+// others.sort(key = sim, reverse = True)  -- stable, so ties keep ascending x -- and the first k ids.
+// One block per requested row; k rounds of "best element strictly after the previous pick in
+// (sim desc, x asc) order", block-wide arg-max through warp shuffles + one shared-memory stage.
+// ------------------------------------------------------------------------------------------------
+constexpr int TOPK_THREADS = 1024;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+row_topk_kernel(const double* __restrict__ sim, int64_t sim_ld, int64_t n_x, const int32_t* __restrict__ rows, int k,
+                int32_t* __restrict__ out) {
+    __shared__ double ws[32];
+    __shared__ int wi[32];
+    __shared__ double pick_s;
+    __shared__ int pick_i;
+    const int32_t row = rows[blockIdx.x];
+    int32_t* o = out + (size_t)blockIdx.x * k;
+    if (row < 0 || row >= n_x) {
+        for (int t = threadIdx.x; t < k; t += blockDim.x) o[t] = -1;
+        return;
+    }
+    const double* srow = sim + (size_t)row * (size_t)sim_ld;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double last_s = 0.0;
+    int last_i = -1;
+    for (int t = 0; t < k; ++t) {
+        double bs = 0.0;
+        int bi = -1;
+        for (int64_t x = threadIdx.x; x < n_x; x += blockDim.x) {
+            if (x == row) continue;
+            const double s = srow[x];
+            const bool after = last_i < 0 || s < last_s || (s == last_s && x > last_i);
+            if (after && (bi < 0 || s > bs)) { bs = s; bi = (int)x; }  // ascending x: first max wins
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double os = __shfl_xor_sync(0xFFFFFFFFu, bs, off);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
+            if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+        }
+        if (lane == 0) { ws[w] = bs; wi[w] = bi; }
+        __syncthreads();
+        if (w == 0) {
+            bs = lane < (blockDim.x >> 5) ? ws[lane] : 0.0;
+            bi = lane < (blockDim.x >> 5) ? wi[lane] : -1;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double os = __shfl_xor_sync(0xFFFFFFFFu, bs, off);
+                const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
+                if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+            }
+            if (lane == 0) { pick_s = bs; pick_i = bi; o[t] = bi; }
+        }
+        __syncthreads();
+        last_s = pick_s;
+        last_i = pick_i;
+        if (last_i < 0) {  // fewer than k other entries (or only NaNs left): pad with -1
+            for (int r = t + 1 + threadIdx.x; r < k; r += blockDim.x) o[r] = -1;
+            return;
+        }
+    }
+}
+
+int get_neighbors_dev(int64_t n_x, const double* sim, int64_t sim_ld, int64_t n_rows, const int32_t* rows, int k,
+                      int32_t* out, cudaStream_t st) {
+    if (n_rows <= 0 || k <= 0) return SB2_OK;
+    if (!sim || !rows || !out || sim_ld < n_x) {
+        set_error("get_neighbors: invalid argument");
+        return SB2_ERR_INVALID;
+    }
+    row_topk_kernel<<<(unsigned)n_rows, TOPK_THREADS, 0, st>>>(sim, sim_ld, n_x, rows, k, out);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
 }  // namespace sb2

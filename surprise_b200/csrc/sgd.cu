@@ -1043,9 +1043,16 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         PP_CUDA(cudaMemcpyAsync(&max_raters, maxc, 4, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
         cleanup2();
-        // y_j is applied `chunks` times per epoch: a popular item must not receive more than ~32 raters'
-        // accumulated gradients in one step (tools/proto/svdpp_variants.py, DESIGN.md "SVD++")
-        p->chunks = std::max(1, std::min(B, (int)ceil_div(max_raters, 32)));
+        // y_j is applied `chunks` times per epoch.  One application per epoch is the schedule that mirrors the
+        // reference: it walks the ratings user by user, so a user's own pushes on the y_j of I_u are all present
+        // while that user's ratings are processed (here: z_u advanced in the user row) and, for items with many
+        // raters, are decayed away by the other users' updates before the user is seen again (here: the
+        // exactly-integrated decay of svdpp_item_apply_kernel + the z_u refresh).  Measured against the
+        // sequential oracle at the full ml-10M shape (tests/golden/svdpp_oracle_rmse.json): 1 application
+        // 0.8381 vs 0.8380; 2..32 applications 0.847..0.866 (the mid-epoch refresh cuts the own-push
+        // accumulation short); DESIGN.md "SVD++".
+        (void)max_raters;
+        p->chunks = 1;
         if (const char* e = getenv("SB2_SVDPP_CHUNKS")) {
             const int c = atoi(e);
             if (c >= 1) p->chunks = std::min(c, B);

@@ -168,9 +168,15 @@ class AlgoBase(object):
 
     def get_neighbors(self, iid, k):
         """Inner ids of the k most similar users / items (algo_base.py:303-334): stable sort of the sim
-        row in descending order, self excluded."""
+        row in descending order, self excluded.  Runs on the device-resident matrix when the algorithm keeps
+        one (the k-NN family); a user-assigned host ``sim`` is uploaded once by ``_sim_device``."""
+        from .. import _native as nat
         n = self.trainset.n_users if self.sim_options["user_based"] else self.trainset.n_items
-        row = np.asarray(self.sim[iid])
-        others = [(x, row[x]) for x in range(n) if x != iid]
-        others.sort(key=lambda t: t[1], reverse=True)
-        return [j for (j, _) in others[:k]]
+        sim = self._sim_device() if hasattr(self, "_sim_device") else nat.to_dev(np.asarray(self.sim), np.float64)
+        k = max(0, min(int(k), n - 1))
+        if k == 0:
+            return []
+        rows = nat.to_dev(np.array([int(iid)], dtype=np.int32), np.int32)
+        out = nat.empty_dev((1, k), np.int32)
+        nat.check(nat.lib().sb2_get_neighbors_dev(n, nat.ptr(sim), n, 1, nat.ptr(rows), k, nat.ptr(out), nat.stream()))
+        return [int(j) for j in out.cpu().numpy()[0] if j >= 0]

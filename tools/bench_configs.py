@@ -90,7 +90,11 @@ if "c4" in which:
     svd = sb.SVD(n_factors=20, lr_all=.007, random_state=0)
     t3, _ = sync_time(lambda: svd.fit(ts))
     est2, _ = svd._estimate_batch(tu, ti)
-    out["c4"] = {"workload": "SVD++ f=20 20 epochs, %dx%d, %d ratings (ml-10M shape x%.2f)" % (ts.n_users, ts.n_items, len(r), scale),
+    gold = os.path.join(ROOT, "tests", "golden", "svdpp_oracle_rmse.json")
+    oracle_rmse = {r_["scale"]: r_ for r_ in json.load(open(gold))["runs"]}.get(scale) if os.path.exists(gold) else None
+    out["c4"] = {"oracle_heldout_rmse": oracle_rmse and oracle_rmse["oracle_svdpp_heldout_rmse"],
+                 "oracle_c_port_cpu_s": oracle_rmse and oracle_rmse["cpu_s"],
+                 "workload": "SVD++ f=20 20 epochs, %dx%d, %d ratings (ml-10M shape x%.2f)" % (ts.n_users, ts.n_items, len(r), scale),
                  "fit_s_first": t1, "fit_s": t2, "updates_per_s": len(r) * 20 / t2, "heldout_rmse": rmse,
                  "svd_f20_fit_s": t3, "svd_f20_updates_per_s": len(r) * 20 / t3,
                  "svd_f20_heldout_rmse": float(np.sqrt(np.mean((np.clip(est2, 0.5, 5) - tr) ** 2)))}
