@@ -61,33 +61,71 @@ def sgd_params(nat, mu, n_epochs=N_EPOCHS):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every ~2 ms (the timed region of the
+    default run is ~130 ms, too short for `nvidia-smi -lms`); falls back to nvidia-smi when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.reason_bits, self.max_mhz, self.halt = [], 0, None, threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                try:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+                except TypeError:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self.halt.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    self.reason_bits |= int(get_reasons(self.handle))
+                except Exception:
+                    break
+                time.sleep(0.002)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
             pass
 
     def stop(self):
+        self.halt.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
+        if self.nvml is not None:
+            # NVML clocks-event-reason bits (nvml.h): sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            reasons = sorted(k for k, v in bits.items() if self.reason_bits & v)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_gbs():

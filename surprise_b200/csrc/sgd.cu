@@ -105,6 +105,12 @@ __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <bool SMEM>
 __device__ __forceinline__ float4 row_ld4(const float* p) {
     if (SMEM) return *reinterpret_cast<const float4*>(p);
@@ -127,29 +133,31 @@ __device__ __forceinline__ void sc_st(float* p, float v) {
 }
 
 // one rating update by a group of G lanes (all lanes hold the same ul / il / r).
-// FAST: n_factors <= 16 * G, four 128-bit chunks per lane, the rows stay in registers between the dot product
-// and the update (few lanes per rating = many ratings per warp instruction: the update phase is bound by
-// instruction issue, profiles/r1_summary.md).  Otherwise 32 lanes stride over the chunks and re-read the rows.
+// CH > 0 (fast path): lane gl owns the 128-bit chunks gl, gl + G, .., gl + (CH - 1) G of the rows and keeps them in
+// registers between the dot product and the update.  (G, CH) are chosen so that (CH - 1) G < F4 <= CH G: only the
+// last chunk can be ragged, every other load / store is unconditional.  Lanes carrying a dummy rating
+// (valid == false, row 0) run the same instruction stream with their stores predicated off, so warps stay
+// converged and the shuffles use the full mask.
+// CH == 0: 32 lanes stride over the chunks and re-read the rows (rows longer than 256 floats).
 // PP (SVD++): the user row is [p | z | g]: z = sum_{j in I_u} y_j / sqrt|I_u| as of the last y_j application,
 // advanced by the user's own updates (z += lr_yj (err q - reg_yj z), which is exactly what the reference's
 // per-rating y_j updates do to that sum); g accumulates err * q / sqrt|I_u| for the next y_j application.
-template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
+template <int G, int CH, bool SU, bool SI, bool BIASED, bool PP>
 __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float* qrow, float* bup, float* bip,
                                            const float* isqp, float* cntp, float r, int gl, bool valid, int F4) {
     constexpr unsigned gmask = 0xFFFFFFFFu;  // callers keep whole warps converged (dummy ratings: valid == false)
     const int FP = F4 * 4;
-    if (FAST) {
-        // CH = 4 chunks of 128 bits per lane: chunk index gl + c * G
-        constexpr int CH = 4;
+    if (CH > 0) {
+        constexpr int NCH = CH > 0 ? CH : 1;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 p[CH], q[CH], z[CH], g[CH];
-        bool act[CH];
+        const bool tail_ok = gl + (NCH - 1) * G < F4;
+        float4 p[NCH], q[NCH], z[NCH], g[NCH];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             const int ch = gl + c * G;
-            act[c] = valid && ch < F4;
+            const bool ok = (c + 1 < NCH) || tail_ok;
             p[c] = q[c] = z[c] = g[c] = zero4;
-            if (act[c]) {
+            if (ok) {
                 p[c] = row_ld4<SU>(prow + 4 * ch);
                 q[c] = row_ld4<SI>(qrow + 4 * ch);
                 if (PP) {
@@ -167,20 +175,24 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
             isq = sc_ld<SU>(isqp);
             cnt = sc_ld<SU>(cntp);
         }
-        float dot = 0.f;
+        float part[NCH];
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             if (PP) { p[c].x += z[c].x; p[c].y += z[c].y; p[c].z += z[c].z; p[c].w += z[c].w; }  // p <- p + z
-            dot += (p[c].x * q[c].x + p[c].y * q[c].y) + (p[c].z * q[c].z + p[c].w * q[c].w);
+            part[c] = (p[c].x * q[c].x + p[c].y * q[c].y) + (p[c].z * q[c].z + p[c].w * q[c].w);
         }
+        float dot = part[0];
+        if (NCH == 2) dot = part[0] + part[1];
+        if (NCH == 3) dot = (part[0] + part[1]) + part[2];
+        if (NCH == 4) dot = (part[0] + part[1]) + (part[2] + part[3]);
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
         const float err = BIASED ? r - (a.mu + b_u + b_i + dot) : r - dot;
         const float eg = err * isq;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            if (!act[c]) continue;
+        for (int c = 0; c < NCH; ++c) {
             const int ch = gl + c * G;
+            const bool st = valid && ((c + 1 < NCH) || tail_ok);
             const float4 pz = p[c];  // p (+ z for SVD++)
             float4 po = pz;
             if (PP) { po.x -= z[c].x; po.y -= z[c].y; po.z -= z[c].z; po.w -= z[c].w; }
@@ -193,8 +205,10 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
             qn.y = q[c].y + a.lr_qi * (err * pz.y - a.reg_qi * q[c].y);
             qn.z = q[c].z + a.lr_qi * (err * pz.z - a.reg_qi * q[c].z);
             qn.w = q[c].w + a.lr_qi * (err * pz.w - a.reg_qi * q[c].w);
-            row_st4<SU>(prow + 4 * ch, pn);
-            row_st4<SI>(qrow + 4 * ch, qn);
+            if (st) {
+                row_st4<SU>(prow + 4 * ch, pn);
+                row_st4<SI>(qrow + 4 * ch, qn);
+            }
             if (PP) {
                 float4 zn, gn;
                 zn.x = z[c].x + a.lr_yj * (err * q[c].x - a.reg_yj * z[c].x);
@@ -203,8 +217,10 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
                 zn.w = z[c].w + a.lr_yj * (err * q[c].w - a.reg_yj * z[c].w);
                 gn.x = g[c].x + eg * q[c].x; gn.y = g[c].y + eg * q[c].y;
                 gn.z = g[c].z + eg * q[c].z; gn.w = g[c].w + eg * q[c].w;
-                row_st4<SU>(prow + FP + 4 * ch, zn);
-                row_st4<SU>(prow + 2 * FP + 4 * ch, gn);
+                if (st) {
+                    row_st4<SU>(prow + FP + 4 * ch, zn);
+                    row_st4<SU>(prow + 2 * FP + 4 * ch, gn);
+                }
             }
         }
         if (gl == 0 && valid) {
@@ -277,14 +293,19 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
 }
 
 // G lanes per rating, SU / SI: user / item block staged in shared memory, BIASED: SVD(biased=True)
-template <int G, bool FAST, bool SU, bool SI, bool BIASED, bool PP>
-__global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
+// threads per CTA: 512 for G >= 16 (rows of 132..256 floats), else 256.  1024 threads would cap the kernel at 64
+// registers, which the ring state alone nearly fills (spills).
+__host__ __device__ constexpr int dsgd_threads(int g) { return g >= 16 ? 512 : 256; }
+
+template <int G, int CH, bool SU, bool SI, bool BIASED, bool PP>
+__global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const DsgdArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int B = a.B, W = a.W, FP = a.FP, F4 = a.FP >> 2;
     const int US = a.US, U4 = a.US >> 2;  // user rows: US floats ([p] or [p | z | g])
     const int ub = blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int gid = tid / G, gl = tid % G;
+    const int gid0 = (tid & ~31) / G;  // first lane-group of this warp
 
     // shared memory carve-up
     // item-block buffers: [max_il x FP factors | max_il biases], two of them when blocks hop through DSMEM
@@ -294,10 +315,10 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     float* isq_s = bu_s + (SU ? a.max_ul : 0);
     float* cnt_s = isq_s + ((SU && PP) ? a.max_ul : 0);
     int* wave_s = reinterpret_cast<int*>(cnt_s + ((SU && PP) ? a.max_ul : 0));
-    int* coff_s = wave_s + (NW + 1);          // [2 * B]: cell begin / end per stratum
-    int* rul_s = coff_s + 2 * B;
-    int* ril_s = rul_s + a.rec_cap;
-    float* rr_s = reinterpret_cast<float*>(ril_s + a.rec_cap);
+    int* coff_s = wave_s + 2 * (NW + 1);      // [2 * B]: cell begin / end per stratum (wave_s: two buffers)
+    int* rul_s = coff_s + 2 * B;              // records: two buffers of rec_cap each
+    int* ril_s = rul_s + 2 * a.rec_cap;
+    float* rr_s = reinterpret_cast<float*>(ril_s + 2 * a.rec_cap);
 
     // ring mailboxes (clusters): bar_data = "my right neighbour's push has landed in my spare buffer",
     // bar_free = "my left neighbour has finished reading the buffer I am about to overwrite"
@@ -331,6 +352,9 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
     __syncthreads();
 
     long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, n_wave = 0, t_hop = 0;
+#ifdef SB2_DSGD_WAVE_PROF
+    long long t_act = 0, t_bar = 0;  // warp 0: cycles inside the updates of a wave / in the barrier after it
+#endif
     // Two-level ring.  CTAs form clusters of C; cluster Cl owns user blocks Cl*C .. Cl*C+C-1.  Item blocks form
     // K = B / C super-blocks of C blocks.  Outer step T: super-block D = (Cl + T) % K is resident in the
     // cluster; inner step t: CTA c updates item block (D, (c + t) % C) and then pushes it into its left
@@ -351,142 +375,176 @@ __global__ void __launch_bounds__(256, 1) dsgd_svd_kernel(const DsgdArgs a) {
         left_data_bar = dsmem_addr(&ring_bar[0], (uint32_t)(c == 0 ? C - 1 : c - 1));
         right_free_bar = dsmem_addr(&ring_bar[2], (uint32_t)(c + 1 == C ? 0 : c + 1));
     }
-    for (int ep = 0; ep < a.n_epochs; ++ep) {
-        for (int T = T_begin; T < T_end; ++T) {
-            const int D = (Cl + T) % K;
-            const int gstep = ep * n_outer + (T - T_begin);
-            const int t_lo = max(0, a.s_begin - T * C), t_hi = min(C, a.s_end - T * C);
-            for (int t = t_lo; t < t_hi; ++t) {
-                const int s = T * C + t;
-                const bool first = (t == t_lo), last = (t + 1 == t_hi);  // of this outer step within the launch
-                const bool wait_flag = first && !(ep == 0 && T == T_begin);
-                int j = c + t;
-                if (j >= C) j -= C;
-                const int ib = D * C + j;
-                float* qi_s = ibuf_s + (size_t)slot * a.ibuf;
-                float* bi_s = qi_s + (size_t)a.max_il * FP;
-                const long long c0 = clock64();
-                // this stratum's records and wave table do not depend on the ring: fetch them while waiting
-                const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
-                const int staged = min(cnt, a.rec_cap);
-                for (int x = tid; x < staged; x += nthr) {
-                    rul_s[x] = a.ul[k0 + x];
-                    ril_s[x] = a.il[k0 + x];
-                    rr_s[x] = a.r[k0 + x];
-                }
-                for (int x = tid; x <= NW; x += nthr) wave_s[x] = a.wave_off[((size_t)s * B + ub) * (NW + 1) + x];
-                if (wait_flag && tid == 0) {
-                    while (ld_relaxed(a.flags + ib) != gstep) { /* previous cluster still owns the super-block */ }
-                    fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
-                }
-                __syncthreads();
-                const long long c1 = clock64();
-                const int ni_local = (a.n_items - ib + B - 1) / B;
-                if (SI && first) {
-                    const int total = ni_local * F4;
-                    for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
-                        float4 v[4];
+    const int n_strata = a.s_end - a.s_begin;
+    const int n_steps = a.n_epochs * n_strata;
+    // records + wave table of step j go to buffer (j & 1) with cp.async, issued one step ahead: they land while
+    // the previous stratum is being updated instead of costing an L2 round trip at the head of every stratum
+    auto prefetch = [&](int j) {
+        const int s = a.s_begin + j % n_strata;
+        const int k0 = coff_s[2 * s];
+        const int staged = min(coff_s[2 * s + 1] - k0, a.rec_cap);
+        int* rul = rul_s + (size_t)(j & 1) * a.rec_cap;
+        int* ril = ril_s + (size_t)(j & 1) * a.rec_cap;
+        float* rr = rr_s + (size_t)(j & 1) * a.rec_cap;
+        int* wave = wave_s + (j & 1) * (NW + 1);
+        for (int x = tid; x < staged; x += nthr) {
+            cp_async4(rul + x, a.ul + k0 + x);
+            cp_async4(ril + x, a.il + k0 + x);
+            cp_async4(rr + x, a.r + k0 + x);
+        }
+        const int* wsrc = a.wave_off + ((size_t)s * B + ub) * (NW + 1);
+        for (int x = tid; x <= NW; x += nthr) cp_async4(wave + x, wsrc + x);
+    };
+    if (n_steps > 0) prefetch(0);
+    for (int step = 0; step < n_steps; ++step) {
+        const int ep = step / n_strata;
+        const int s = a.s_begin + (step - ep * n_strata);
+        const int T = s / C, t = s - T * C;
+        const int D = (Cl + T) % K;
+        const int gstep = ep * n_outer + (T - T_begin);
+        const bool first = (s == a.s_begin) || t == 0;       // of this outer step within the launch
+        const bool last = (s + 1 == a.s_end) || t + 1 == C;
+        const bool wait_flag = first && step != 0;
+        const int* rul_c = rul_s + (size_t)(step & 1) * a.rec_cap;
+        const int* ril_c = ril_s + (size_t)(step & 1) * a.rec_cap;
+        const float* rr_c = rr_s + (size_t)(step & 1) * a.rec_cap;
+        const int* wave_c = wave_s + (step & 1) * (NW + 1);
+        int j = c + t;
+        if (j >= C) j -= C;
+        const int ib = D * C + j;
+        float* qi_s = ibuf_s + (size_t)slot * a.ibuf;
+        float* bi_s = qi_s + (size_t)a.max_il * FP;
+        const long long c0 = clock64();
+        const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
+        const int staged = min(cnt, a.rec_cap);
+        cp_async_wait_all();  // this stratum's records (issued during the previous stratum)
+        if (wait_flag && tid == 0) {
+            while (ld_relaxed(a.flags + ib) != gstep) { /* previous cluster still owns the super-block */ }
+            fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
+        }
+        __syncthreads();
+        if (step + 1 < n_steps) prefetch(step + 1);
+        const long long c1 = clock64();
+        const int ni_local = (a.n_items - ib + B - 1) / B;
+        if (SI && first) {
+            const int total = ni_local * F4;
+            for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
+                float4 v[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int x = t0 + q * nthr;
-                            if (x < total) {
-                                const int l = x / F4, cc = x - l * F4;
-                                v[q] = __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc);
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int x = t0 + q * nthr;
-                            if (x < total) reinterpret_cast<float4*>(qi_s)[x] = v[q];
-                        }
+                for (int q = 0; q < 4; ++q) {
+                    const int x = t0 + q * nthr;
+                    if (x < total) {
+                        const int l = x / F4, cc = x - l * F4;
+                        v[q] = __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc);
                     }
-                    for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
-                    __syncthreads();
                 }
-                const long long c2 = clock64();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = t0 + q * nthr;
+                    if (x < total) reinterpret_cast<float4*>(qi_s)[x] = v[q];
+                }
+            }
+            for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
+            __syncthreads();
+        }
+        const long long c2 = clock64();
 
-                // every lane-group runs the same (CTA-uniform) number of rounds per wave, groups beyond the wave's
-                // end carry a dummy rating with all stores predicated off: control flow stays warp-uniform, so the
-                // shuffles can use the full-warp mask (a per-group mask costs MATCH / VOTE instructions per shuffle)
-                auto process = [&](int k, bool valid) {
-                    int ul = 0, il = 0;
-                    float r = 0.f;
-                    if (valid) {
-                        if (k < staged) { ul = rul_s[k]; il = ril_s[k]; r = rr_s[k]; }
-                        else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
+        // every lane-group runs the same (CTA-uniform) number of rounds per wave, groups beyond the wave's
+        // end carry a dummy rating with all stores predicated off: control flow stays warp-uniform, so the
+        // shuffles can use the full-warp mask (a per-group mask costs MATCH / VOTE instructions per shuffle)
+        auto process = [&](int k, bool valid) {
+            int ul = 0, il = 0;
+            float r = 0.f;
+            if (valid) {
+                if (k < staged) { ul = rul_c[k]; il = ril_c[k]; r = rr_c[k]; }
+                else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
+            }
+            float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
+            float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
+            float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
+            float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
+            const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
+            float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
+            sgd_update<G, CH, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, valid, F4);
+        };
+        for (int w = 0; w < NW - 1; ++w) {
+            const int wb = wave_c[w], we = wave_c[w + 1];
+            if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
+            // a warp whose first lane-group is already past the wave's end holds only dummies: skip it
+            // (warp-uniform test), it would otherwise compete for issue slots with the working warps
+#ifdef SB2_DSGD_WAVE_PROF
+            const long long w0 = clock64();
+#endif
+            for (int k = wb; k < we; k += W)
+                if (k + gid0 < we) process(k + gid, k + gid < we);
+            ++n_wave;
+#ifdef SB2_DSGD_WAVE_PROF
+            const long long w1 = clock64();
+            __syncthreads();
+            t_act += w1 - w0;
+            t_bar += clock64() - w1;
+#else
+            __syncthreads();
+#endif
+        }
+        {
+            const int wb = wave_c[NW - 1], we = wave_c[NW];
+            if (wb != we) {  // sequential tail (colour overflow), the first warp replays it in order
+                if (tid < 32)
+                    for (int k = wb; k < we; ++k) {
+                        process(k, gid == 0);
+                        __syncwarp();  // consecutive tail ratings may share a row
                     }
-                    float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
-                    float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
-                    float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
-                    float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
-                    const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
-                    float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
-                    sgd_update<G, FAST, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, valid, F4);
-                };
-                for (int w = 0; w < NW - 1; ++w) {
-                    const int wb = wave_s[w], we = wave_s[w + 1];
-                    if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
-                    for (int k = wb; k < we; k += W) process(k + gid, k + gid < we);
-                    ++n_wave;
-                    __syncthreads();
-                }
-                {
-                    const int wb = wave_s[NW - 1], we = wave_s[NW];
-                    if (wb != we) {  // sequential tail (colour overflow), the first warp replays it in order
-                        if (tid < 32)
-                            for (int k = wb; k < we; ++k) {
-                                process(k, gid == 0);
-                                __syncwarp();  // consecutive tail ratings may share a row
-                            }
-                        __syncthreads();
-                    }
-                }
-                const long long c3 = clock64();
-                if (!last) {
-                    // fast hop (neighbour-to-neighbour, no cluster-wide barrier): once the left neighbour has finished
-                    // reading its spare buffer (its previous push), copy my block into it through distributed shared
-                    // memory, tell it the data is there, tell my right neighbour that my block buffer is reusable,
-                    // and wait for my right neighbour's push into my own spare buffer.
-                    if (n_push > 0 && tid == 0) mbar_wait_cluster(&ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
-                    __syncthreads();
-                    const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
-                    const int n4 = a.ibuf >> 2;
-                    for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
-                    __syncthreads();  // all of this CTA's remote stores precede thread 0's cluster-scope releases
-                    if (tid == 0) {
-                        mbar_arrive_remote(left_data_bar + 8u * (n_push & 1));
-                        mbar_arrive_remote(right_free_bar + 8u * (n_push & 1));
-                        mbar_wait_cluster(&ring_bar[n_push & 1], (n_push >> 1) & 1);
-                    }
-                    __syncthreads();
-                    ++n_push;
-                    slot ^= 1;
-                    t_hop += clock64() - c3;
-                } else {
-                    // slow hop: hand the block to the next cluster through L2
-                    if (SI) {
-                        for (int l = tid / F4, cc = tid % F4; l < ni_local; ) {
-                            __stcg(reinterpret_cast<float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc,
-                                   reinterpret_cast<const float4*>(qi_s)[l * F4 + cc]);
-                            cc += nthr % F4; l += nthr / F4;
-                            if (cc >= F4) { cc -= F4; ++l; }
-                        }
-                        if (BIASED)
-                            for (int l = tid; l < ni_local; l += nthr) __stcg(a.bi + ib + (size_t)l * B, bi_s[l]);
-                    }
-                    // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
-                    __syncthreads();
-                    if (tid == 0) st_release(a.flags + ib, gstep + 1);
-                    t_wb += clock64() - c3;
-                }
-                t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2;
+                __syncthreads();
             }
         }
+        const long long c3 = clock64();
+        if (!last) {
+            // fast hop (neighbour-to-neighbour, no cluster-wide barrier): once the left neighbour has finished
+            // reading its spare buffer (its previous push), copy my block into it through distributed shared
+            // memory, tell it the data is there, tell my right neighbour that my block buffer is reusable,
+            // and wait for my right neighbour's push into my own spare buffer.
+            if (n_push > 0 && tid == 0) mbar_wait_cluster(&ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
+            __syncthreads();
+            const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
+            const int n4 = a.ibuf >> 2;
+            for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
+            __syncthreads();  // all of this CTA's remote stores precede thread 0's cluster-scope releases
+            if (tid == 0) {
+                mbar_arrive_remote(left_data_bar + 8u * (n_push & 1));
+                mbar_arrive_remote(right_free_bar + 8u * (n_push & 1));
+                mbar_wait_cluster(&ring_bar[n_push & 1], (n_push >> 1) & 1);
+            }
+            __syncthreads();
+            ++n_push;
+            slot ^= 1;
+            t_hop += clock64() - c3;
+        } else {
+            // slow hop: hand the block to the next cluster through L2
+            if (SI) {
+                for (int l = tid / F4, cc = tid % F4; l < ni_local; ) {
+                    __stcg(reinterpret_cast<float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc,
+                           reinterpret_cast<const float4*>(qi_s)[l * F4 + cc]);
+                    cc += nthr % F4; l += nthr / F4;
+                    if (cc >= F4) { cc -= F4; ++l; }
+                }
+                if (BIASED)
+                    for (int l = tid; l < ni_local; l += nthr) __stcg(a.bi + ib + (size_t)l * B, bi_s[l]);
+            }
+            // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
+            __syncthreads();
+            if (tid == 0) st_release(a.flags + ib, gstep + 1);
+            t_wb += clock64() - c3;
+        }
+        t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2;
     }
     if (C > 1) cluster_sync_all();  // no CTA leaves while a neighbour may still address its shared memory
     if (a.prof != nullptr && tid == 0) {
         a.prof[ub * 8 + 0] = t_wait; a.prof[ub * 8 + 1] = t_load; a.prof[ub * 8 + 2] = t_upd; a.prof[ub * 8 + 3] = t_wb;
         a.prof[ub * 8 + 4] = t_upd; a.prof[ub * 8 + 5] = n_wave; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = t_hop;
+#ifdef SB2_DSGD_WAVE_PROF
+        a.prof[ub * 8 + 4] = t_act; a.prof[ub * 8 + 5] = t_bar;
+#endif
     }
     if (SU) {
         for (int l = tid / U4, c = tid % U4; l < nu_local; ) {
@@ -679,7 +737,7 @@ __global__ void f32_to_f64_kernel(int64_t n, const float* __restrict__ src, doub
 struct sb2_svd_plan {
     int64_t n_users = 0, n_items = 0, n = 0;
     sb2_sgd_params prm;
-    int B = 0, W = 0, G = 0, FP = 0;
+    int B = 0, W = 0, G = 0, CH = 0, FP = 0;  // W lane-groups of G lanes, CH 128-bit chunks per lane (0: strided)
     bool stage_u = false, stage_i = false, fast = true;
     size_t smem = 0;
     int *ul = nullptr, *il = nullptr, *off = nullptr, *wave_off = nullptr, *flags = nullptr;
@@ -701,32 +759,36 @@ namespace sb2 {
 
 typedef void (*dsgd_kernel_t)(const DsgdArgs);
 
-template <int G, bool FAST>
+template <int G, int CH>
 static dsgd_kernel_t dsgd_kernel_g(const sb2_svd_plan* p) {
     // staging plans: both blocks in shared memory, item block only, or neither.  SVD++ is always biased.
     if (p->with_yj) {
-        if (p->stage_u && p->stage_i) return dsgd_svd_kernel<G, FAST, true, true, true, true>;
-        if (p->stage_i) return dsgd_svd_kernel<G, FAST, false, true, true, true>;
-        return dsgd_svd_kernel<G, FAST, false, false, true, true>;
+        if (p->stage_u && p->stage_i) return dsgd_svd_kernel<G, CH, true, true, true, true>;
+        if (p->stage_i) return dsgd_svd_kernel<G, CH, false, true, true, true>;
+        return dsgd_svd_kernel<G, CH, false, false, true, true>;
     }
     const bool b = p->prm.biased != 0;
     if (p->stage_u && p->stage_i)
-        return b ? dsgd_svd_kernel<G, FAST, true, true, true, false> : dsgd_svd_kernel<G, FAST, true, true, false, false>;
+        return b ? dsgd_svd_kernel<G, CH, true, true, true, false> : dsgd_svd_kernel<G, CH, true, true, false, false>;
     if (p->stage_i)
-        return b ? dsgd_svd_kernel<G, FAST, false, true, true, false> : dsgd_svd_kernel<G, FAST, false, true, false, false>;
-    return b ? dsgd_svd_kernel<G, FAST, false, false, true, false> : dsgd_svd_kernel<G, FAST, false, false, false, false>;
+        return b ? dsgd_svd_kernel<G, CH, false, true, true, false> : dsgd_svd_kernel<G, CH, false, true, false, false>;
+    return b ? dsgd_svd_kernel<G, CH, false, false, true, false> : dsgd_svd_kernel<G, CH, false, false, false, false>;
+}
+
+// instantiated (G, CH): G is the power of two >= F4 / 4, so CH = ceil(F4 / G) is 3 or 4 (1..4 for G = 1)
+static bool dsgd_shape_ok(int g, int ch) {
+    if (g == 1) return ch >= 1 && ch <= 4;
+    return (g == 2 || g == 4 || g == 8 || g == 16) && (ch == 3 || ch == 4);
 }
 
 static dsgd_kernel_t dsgd_kernel(const sb2_svd_plan* p) {
-    if (!p->fast) return dsgd_kernel_g<32, false>(p);
-    switch (p->G) {
-        case 1: return dsgd_kernel_g<1, true>(p);
-        case 2: return dsgd_kernel_g<2, true>(p);
-        case 4: return dsgd_kernel_g<4, true>(p);
-        case 8: return dsgd_kernel_g<8, true>(p);
-        case 16: return dsgd_kernel_g<16, true>(p);
-        default: return dsgd_kernel_g<32, true>(p);
-    }
+    if (!p->fast) return dsgd_kernel_g<32, 0>(p);
+#define SB2_DSGD_CASE(g, ch) \
+    if (p->G == g && p->CH == ch) return dsgd_kernel_g<g, ch>(p);
+    SB2_DSGD_CASE(1, 1) SB2_DSGD_CASE(1, 2) SB2_DSGD_CASE(1, 3) SB2_DSGD_CASE(1, 4) SB2_DSGD_CASE(2, 3) SB2_DSGD_CASE(2, 4)
+    SB2_DSGD_CASE(4, 3) SB2_DSGD_CASE(4, 4) SB2_DSGD_CASE(8, 3) SB2_DSGD_CASE(8, 4) SB2_DSGD_CASE(16, 3) SB2_DSGD_CASE(16, 4)
+#undef SB2_DSGD_CASE
+    return nullptr;
 }
 
 static void dsgd_launch_config(const sb2_svd_plan* p, int n_blocks, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr,
@@ -805,19 +867,29 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     p->FP = (int)round_up(f, 4);
     p->US = p->with_yj ? 3 * p->FP : p->FP;
     const int F4 = p->FP / 4;
-    // lanes per rating: four 128-bit chunks per lane (rows stay in registers); rows longer than 128 factors
-    // fall back to 32 lanes striding the row.
-    p->fast = F4 <= 32;
-    p->G = !p->fast ? 32 : F4 <= 4 ? 1 : F4 <= 8 ? 2 : F4 <= 16 ? 4 : 8;
-    if (const char* e = getenv("SB2_DSGD_LANES")) {
-        const int g = atoi(e);
-        if (p->fast && (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) && g * 4 >= F4) p->G = g;
+    // lanes per rating: G = the power of two >= F4 / 4 (at most 16), CH = ceil(F4 / G) <= 4 chunks of 128 bits per
+    // lane, rows in registers; rows longer than 256 floats fall back to 32 lanes striding the row.  Fewer, fatter
+    // lanes win: with ~13 ratings per wave the critical path is one warp's instruction stream either way, and
+    // wider groups only add shuffle steps and warps per scheduler (measured at f = 100: G = 8 / 16 / 32 ->
+    // 11.7 / 13.1 / 13.8 ms per fit; f = 20: G = 2 / 4 -> 76 / 87 ms at the ml-10M shape; profiles/r1_summary.md).
+    p->fast = F4 <= 64;
+    p->G = 32;
+    p->CH = 0;
+    if (p->fast) {
+        int g = 1;
+        while (g < 16 && 4 * g < F4) g <<= 1;
+        p->G = g;
+        p->CH = (F4 + g - 1) / g;
+        if (const char* e = getenv("SB2_DSGD_LANES")) {
+            const int ge = atoi(e);
+            if (ge > 0 && dsgd_shape_ok(ge, (F4 + ge - 1) / ge)) { p->G = ge; p->CH = (F4 + ge - 1) / ge; }
+        }
     }
-    const int threads = 256;
+    const int threads = dsgd_threads(p->G);
     p->W = threads / p->G;
     if (const char* e = getenv("SB2_DSGD_GROUPS")) {
         const int w = atoi(e);
-        if (w > 0 && w * p->G <= 256 && (w * p->G) % 32 == 0) p->W = w;
+        if (w > 0 && w * p->G <= threads && (w * p->G) % 32 == 0) p->W = w;
     }
     // Blocks B (= CTAs = strata per epoch) and cluster size C.  With thread-block clusters an item block hops
     // CTA -> CTA through distributed shared memory (~1k cycles) and only every C-th hop goes through L2
@@ -830,11 +902,11 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     const size_t budget = 200 * 1024;
     auto plan_smem = [&](int Bc, int Cc, bool* st_i, bool* st_u, size_t* used, int* ibuf) {
         const int mul = (int)ceil_div(n_users, Bc), mil = (int)ceil_div(n_items, Bc);
-        const size_t fixed = (size_t)(NW + 1 + 2 * Bc) * 4 + 64;
+        const size_t fixed = (size_t)(2 * (NW + 1) + 2 * Bc) * 4 + 64;
         *ibuf = (int)round_up((int64_t)mil * (p->FP + 1), 4);
         const size_t need_i = (size_t)(Cc > 1 ? 2 : 1) * *ibuf * sizeof(float) + 16;
         const size_t need_u = (size_t)mul * (p->US + 3) * sizeof(float) + 16;
-        const size_t min_rec = 256 * 12;
+        const size_t min_rec = 256 * 24;
         *st_i = fixed + min_rec + need_i <= budget;
         *st_u = *st_i && fixed + min_rec + need_i + need_u <= budget;
         *used = fixed + (*st_i ? need_i : 0) + (*st_u ? need_u : 0);
@@ -860,7 +932,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         p->B = Bc; p->C = Cc;
         plan_smem(Bc, Cc, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
         if (!p->stage_i) continue;
-        p->smem = smem_used + 256 * 12 + 64;
+        p->smem = smem_used + 256 * 24 + 64;
         dsgd_kernel_t kern = dsgd_kernel(p);
         int max_clusters = 0;
         cudaLaunchConfig_t cfg;
@@ -1061,11 +1133,10 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     // shared-memory plan: wave table + cell offsets, item buffer(s), user block, then as many of a cell's
     // records as still fit (the rest is read from global memory)
     int rec_cap = std::max(status_h[1], 1);
-    rec_cap = (int)std::min<size_t>((size_t)rec_cap, (budget - smem_used) / 12);
-    rec_cap = (int)round_up(rec_cap, 4);
+    rec_cap = (int)std::min<size_t>((size_t)round_up(rec_cap, 4), (budget - smem_used) / 24 / 4 * 4);
     p->rec_cap = rec_cap;
     p->max_cell = status_h[1];
-    p->smem = smem_used + (size_t)rec_cap * 12 + 64;
+    p->smem = smem_used + (size_t)rec_cap * 24 + 64;
     *out = p;
     return SB2_OK;
 }

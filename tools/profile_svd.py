@@ -35,4 +35,6 @@ print("per-CTA cycles (mean over CTAs) wait %.0f load %.0f update %.0f writeback
       % (*m[:4], tot.mean(), np.round(m[:4] / (20 * b.value))))
 print("%.1f waves/stratum; update-phase cycles per wave %.0f; DSMEM hop cycles per stratum %.0f"
       % (m[6] / (20 * b.value), m[2] / max(m[6], 1), m[7] / (20 * b.value)))
+if os.environ.get("WAVE_PROF"):
+    print("warp 0 per wave: update path %.0f cycles, barrier %.0f cycles" % (m[4] / max(m[6], 1), m[5] / max(m[6], 1)))
 lib.sb2_svd_plan_destroy(plan)
