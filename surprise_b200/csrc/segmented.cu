@@ -186,6 +186,75 @@ __global__ void nmf_pass_kernel(int64_t n_seg, int f, const int64_t* __restrict_
     }
 }
 
+// Unbiased model, f <= G: the same pass with est = dot(q_i, p_u) recomputed on the fly instead of read from a
+// materialised array (which costs one extra gather of both factor rows per rating plus an 8-byte scatter into item
+// order, all through L2 / HBM).  The G lanes of a group take G consecutive entries of their segment:
+//   load   (lane = factor): the G gathered rows of the other side go to a shared-memory tile, one coalesced
+//           120-byte read per row -- the only global traffic of the entry;
+//   step A (lane = entry): est = ((0 + q[0] p[0]) + q[1] p[1]) + ... in factor order -- the multiply / add chain of
+//           nmf_dot_kernel, i.e. the reference's `dot` loop (matrix_factorization.pyx:699-702); the lane walks its
+//           row in the tile against the fixed row (broadcast reads); (r, est) of the entry go to shared memory;
+//   step B (lane = factor): for each of the G entries in order, (r, est) is one broadcast read, the row element
+//           comes from the tile, and the two ordered accumulation chains advance.
+// The kernel is bound by the L1TEX data pipe (shared-memory wavefronts; shuffles ride the same pipe), see
+// profiles/r1_summary.md "NMF": values that every lane of the group needs are therefore broadcast reads, not
+// 64-bit shuffles (two SHFL each).  A variant that kept the G row elements in registers and tiled only the
+// products was slower (80 registers, half the resident warps).  Same bits as the three-kernel path (est is the
+// same chain; the accumulation order is unchanged).
+constexpr int NMF_THREADS = 128;
+
+template <int G>
+__global__ void __launch_bounds__(NMF_THREADS)
+nmf_pass_fused_kernel(int64_t n_seg, int f, const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ other_idx,
+                      const double* __restrict__ r_seg, const double* __restrict__ mine_old,
+                      const double* __restrict__ other_old, double* __restrict__ mine_new, double reg, int* status) {
+    __shared__ double tile_s[NMF_THREADS / G][G][G + 1];
+    __shared__ double2 re_s[NMF_THREADS / G][G];
+    __shared__ double mrow_s[NMF_THREADS / G][G];
+    const int gl = threadIdx.x % G, g = threadIdx.x / G;
+    const int64_t seg = blockIdx.x * (int64_t)(NMF_THREADS / G) + g;
+    if (seg >= n_seg) return;  // whole groups leave; the shuffles below name only the lanes of one group
+    const unsigned gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    const int64_t b = seg_ptr[seg], e = seg_ptr[seg + 1];
+    const bool act = gl < f;
+    const double m_l = act ? mine_old[(size_t)seg * f + gl] : 0.0;
+    double (*tile)[G + 1] = tile_s[g];
+    double2* re = re_s[g];
+    double* mrow = mrow_s[g];
+    mrow[gl] = m_l;
+    double n0 = 0.0, d0 = 0.0;
+    for (int64_t a = b; a < e; a += G) {
+        const int64_t mine = a + gl;
+        const bool has = mine < e;
+        const int32_t oi = has ? other_idx[mine] : 0;
+        const double rr = has ? r_seg[mine] : 0.0;
+        const int cnt = (int)((e - a) < (int64_t)G ? (e - a) : (int64_t)G);
+        for (int t = 0; t < cnt; ++t) {
+            const int32_t oit = __shfl_sync(gmask, oi, t, G);
+            if (act) tile[t][gl] = other_old[(size_t)oit * f + gl];
+        }
+        __syncwarp(gmask);
+        double est = 0.0;
+        if (has)
+            for (int j = 0; j < f; ++j) est = __dadd_rn(est, __dmul_rn(tile[gl][j], mrow[j]));
+        re[gl] = make_double2(rr, est);
+        __syncwarp(gmask);
+        for (int t = 0; t < cnt; ++t) {
+            const double2 x = re[t];
+            const double o = act ? tile[t][gl] : 0.0;
+            n0 = __dadd_rn(n0, __dmul_rn(o, x.x));
+            d0 = __dadd_rn(d0, __dmul_rn(o, x.y));
+        }
+        __syncwarp(gmask);  // the next tile overwrites the rows
+    }
+    if (act) {
+        const double nr = (double)(e - b);
+        const double d = __dadd_rn(d0, __dmul_rn(__dmul_rn(nr, reg), m_l));
+        if (d == 0.0) atomicExch(&status[SEG_ZERODIV], 1);
+        mine_new[(size_t)seg * f + gl] = __dmul_rn(m_l, __ddiv_rn(n0, d));
+    }
+}
+
 // biased model: sequential bias recursion + est per rating (all_ratings order), one thread.
 __global__ void nmf_dot_kernel(int64_t n, int f, const int32_t* __restrict__ u, const int32_t* __restrict__ i,
                                const double* __restrict__ pu, const double* __restrict__ qi, double* __restrict__ dot) {
@@ -260,6 +329,28 @@ static int nmf_pass(int64_t n_seg, int f, const int64_t* ptr, const int32_t* idx
     if (f <= 8) return launch_pass<8>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
     if (f <= 16) return launch_pass<16>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
     return launch_pass<32>(n_seg, f, ptr, idx, r, est, mine_old, other_old, mine_new, reg, status, st);
+}
+
+template <int G>
+static int launch_pass_fused(int64_t n_seg, int f, const int64_t* ptr, const int32_t* idx, const double* r,
+                             const double* mine_old, const double* other_old, double* mine_new, double reg, int* status,
+                             cudaStream_t st) {
+    const int gpb = NMF_THREADS / G;
+    nmf_pass_fused_kernel<G><<<(unsigned)ceil_div(n_seg, gpb), NMF_THREADS, 0, st>>>(n_seg, f, ptr, idx, r, mine_old,
+                                                                                     other_old, mine_new, reg, status);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+// f <= 32 only
+static int nmf_pass_fused(int64_t n_seg, int f, const int64_t* ptr, const int32_t* idx, const double* r,
+                          const double* mine_old, const double* other_old, double* mine_new, double reg, int* status,
+                          cudaStream_t st) {
+    if (n_seg <= 0) return SB2_OK;
+    if (f <= 4) return launch_pass_fused<4>(n_seg, f, ptr, idx, r, mine_old, other_old, mine_new, reg, status, st);
+    if (f <= 8) return launch_pass_fused<8>(n_seg, f, ptr, idx, r, mine_old, other_old, mine_new, reg, status, st);
+    if (f <= 16) return launch_pass_fused<16>(n_seg, f, ptr, idx, r, mine_old, other_old, mine_new, reg, status, st);
+    return launch_pass_fused<32>(n_seg, f, ptr, idx, r, mine_old, other_old, mine_new, reg, status, st);
 }
 
 // est for a range of CSC (item-ordered) entries, recomputed from the factors: dot(q[item], p[user]) in factor
@@ -353,8 +444,7 @@ int nmf_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
                                                     p->r_it.as<double>());
         SB2_LAUNCH_CHECK();
     }
-    SB2_TRY(p->dot.alloc(n1 * 8, st));
-    SB2_TRY(p->est_it.alloc(n1 * 8, st));
+    // dot / est_it (8 bytes per rating each) are only needed by the biased / f > 32 path: allocated on first use
     p->ptr_u_h.resize((size_t)n_users + 1);
     p->ptr_i_h.resize((size_t)n_items + 1);
     SB2_CUDA(cudaMemcpyAsync(p->ptr_u_h.data(), p->ptr_u.p, (size_t)(n_users + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -382,7 +472,19 @@ int nmf_plan_epoch_dev(sb2_nmf_plan* p, const sb2_nmf_params* prm, const double*
     const int64_t eu0 = p->ptr_u_h[(size_t)u0], eu1 = p->ptr_u_h[(size_t)u1];
     const int64_t ei0 = p->ptr_i_h[(size_t)i0], ei1 = p->ptr_i_h[(size_t)i1];
     const double* est_u = p->dot.as<double>();
+    if (!biased && f <= 32 && getenv("SB2_NMF_UNFUSED") == nullptr) {
+        // unbiased: est == dot exactly (mu = bu = bi = 0 and 0 + x == x); recomputed inside the passes
+        SB2_TRY(nmf_pass_fused(u1 - u0, f, p->ptr_u.as<int64_t>() + u0, p->i, p->r, pu_cur + (size_t)u0 * f, qi_cur,
+                               pu_new + (size_t)u0 * f, prm->reg_pu, p->status.as<int>(), st));
+        SB2_TRY(nmf_pass_fused(i1 - i0, f, p->ptr_i.as<int64_t>() + i0, p->u_it.as<int32_t>(), p->r_it.as<double>(),
+                               qi_cur + (size_t)i0 * f, pu_cur, qi_new + (size_t)i0 * f, prm->reg_qi,
+                               p->status.as<int>(), st));
+        return SB2_OK;
+    }
     if (n > 0) {
+        if (!p->dot.p) SB2_TRY(p->dot.alloc((size_t)n * 8, st));
+        if (!p->est_it.p) SB2_TRY(p->est_it.alloc((size_t)n * 8, st));
+        est_u = p->dot.as<double>();
         if (biased) {
             if (!p->est.p) SB2_TRY(p->est.alloc((size_t)n * 8, st));
             const unsigned nb = (unsigned)ceil_div(n, 256);
