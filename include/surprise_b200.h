@@ -272,6 +272,19 @@ int sb2_slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* 
 int sb2_get_neighbors_dev(int64_t n_x, const double* sim, int64_t sim_ld, int64_t n_rows, const int32_t* rows,
                           int k, int32_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row shard of a SYMMETRIC multi-rank similarity build (SURVEY.md 8e "cyclic upper-triangular tile sharding").
+ * Same arguments as sb2_sim_build_dev, but only sim[i][j] with row_begin <= i < row_end and j >= row_begin is
+ * computed (tiles at or above the block diagonal; the shard's own diagonal square is mirrored like the
+ * reference mirrors, similarities.pyx:95).  Columns j < row_begin of sim_out are left untouched: they are
+ * the transposes of blocks computed by the shards before this one (surprise_b200/distributed.py exchanges
+ * them over NCCL).  With row ranges of equal triangular area every rank does 1/N of the single-GPU work.
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_sim_build_upper_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx,
+                            const double* r, int64_t nnz, int rating_denom, int min_support, double global_mean,
+                            const double* x_biases, const double* y_biases, double shrinkage, int64_t row_begin,
+                            int64_t row_end, double* sim_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

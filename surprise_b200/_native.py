@@ -41,6 +41,8 @@ SIGNATURES = {
     "sb2_reset_launch_count": (None, []),
     "sb2_sim_build_dev": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _i64, _int, _int, _dbl, _vp, _vp, _dbl, _i64, _i64,
                                  _vp, _vp]),
+    "sb2_sim_build_upper_dev": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _i64, _int, _int, _dbl, _vp, _vp, _dbl, _i64, _i64,
+                                 _vp, _vp]),
     "sb2_sim_build": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _i64, _int, _int, _dbl, _vp, _vp, _dbl, _i64, _i64,
                              _vp]),
     "sb2_gemm_u8_selftest_dev": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -139,6 +139,8 @@ struct FinArgs {
     double a_shift;
     double inv_d, inv_d2;  // 1/denom, 1/denom^2
     int min_support;
+    int upper;    // row shard computes only columns >= row_begin (tiles at or above the block diagonal)
+    int tile_rows;
     double shrinkage;
     double* sim;  // (row_end-row_begin) x n_x
     int* status;
@@ -226,7 +228,11 @@ __global__ void sim_finalize_rows_kernel(const FinArgs f) {
     const int64_t i = f.row_begin + blockIdx.y;
     if (j >= f.n_x || i >= f.row_end) return;
     double s;
+    if (f.upper && j < f.row_begin) return;  // owned (transposed) by an earlier shard, filled in by the exchange
     if (i == j) s = 1.0;
+    else if (f.upper && j < i && j / f.tile_rows < i / f.tile_rows)
+        // below the block diagonal: the tile was not computed; its mirror (j, i) lies in this shard's planes
+        s = sim_value(f, (size_t)(j - f.plane_row0) * f.ld + i, j, i, false);
     else s = sim_value(f, (size_t)(i - f.plane_row0) * f.ld + j, i, j, i > j);
     f.sim[(size_t)(i - f.row_begin) * f.n_x + j] = s;
 }
@@ -279,7 +285,7 @@ constexpr int KIND_SLOPE_ONE = 4;  // internal: freq + dev of SlopeOne from the 
 static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
                     int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
                     const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
-                    int64_t* freq_out, cudaStream_t st) {
+                    int64_t* freq_out, bool upper, cudaStream_t st) {
     const bool slope = (kind == KIND_SLOPE_ONE);
     if (kind < 0 || kind > 4 || n_x <= 0 || n_y < 0 || nnz < 0 || rating_denom <= 0 || row_begin < 0 ||
         row_end > n_x || row_begin >= row_end) {
@@ -398,7 +404,7 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
         for (int b0 = rb0; b0 < rb1; b0 += band)
             for (int cb = 0; cb < ncb; ++cb)
                 for (int rb = b0; rb < std::min(b0 + band, rb1); ++rb)
-                    if (!full || cb >= rb) tiles.push_back(make_int2(rb, cb));
+                    if ((!full && !upper) || cb >= rb) tiles.push_back(make_int2(rb, cb));
     }
     DevBuf tiles_d;
     SB2_TRY(tiles_d.alloc(tiles.size() * sizeof(int2) + 16, st));
@@ -488,6 +494,7 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
     f.inv_d = 1.0 / (double)rating_denom;
     f.inv_d2 = 1.0 / ((double)rating_denom * (double)rating_denom);
     f.min_support = min_support; f.shrinkage = shrinkage; f.sim = sim_out; f.status = status_d.as<int>();
+    f.upper = (upper && !full) ? 1 : 0; f.tile_rows = TR;
     if (slope) {
         const unsigned nt = (unsigned)ceil_div(n_x, 32);
         slope_finalize_kernel<<<dim3(nt, nt), dim3(32, 8), 0, st>>>(f, freq_out, sim_out);
@@ -525,7 +532,22 @@ int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, cons
         return SB2_ERR_INVALID;
     }
     return sim_core(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
-                    shrinkage, row_begin, row_end, sim_out, nullptr, st);
+                    shrinkage, row_begin, row_end, sim_out, nullptr, false, st);
+}
+
+// row shard of a symmetric multi-rank build: only sim[i][j] with j >= row_begin is computed (tiles at or above the
+// block diagonal, mirrored inside the shard's own diagonal square); the columns before row_begin are the transposes
+// of blocks owned by the shards before this one and are left untouched.
+int sim_build_upper_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
+                        int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
+                        const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
+                        cudaStream_t st) {
+    if (kind < 0 || kind > 3) {
+        set_error("sim_build: invalid argument");
+        return SB2_ERR_INVALID;
+    }
+    return sim_core(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
+                    shrinkage, row_begin, row_end, sim_out, nullptr, true, st);
 }
 
 // SlopeOne.fit (slope_one.pyx:44-80): u_ptr / i_idx / r is the ur CSR (items rated by each user)
@@ -536,7 +558,7 @@ int slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, co
         return SB2_ERR_INVALID;
     }
     return sim_core(KIND_SLOPE_ONE, n_items, n_users, u_ptr, i_idx, r, nnz, 1, 0, 0.0, nullptr, nullptr, 0.0, 0, n_items,
-                    dev_out, freq_out, st);
+                    dev_out, freq_out, false, st);
 }
 
 }  // namespace sb2

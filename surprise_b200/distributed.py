@@ -150,9 +150,14 @@ class RingSVD(object):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# Row-block sharded similarity build: every rank packs the (replicated) rating CSR and
-# builds rows [row_begin, row_end) of the n_x x n_x matrix; there is no data-path collective.  Row blocks are
-# multiples of the 256-row tile of the CTA-pair MMA kernel.
+# Row-block sharded similarity build.  Every rank packs the (replicated) rating CSR.
+#   symmetric=True (default): rank k owns rows [b_k, b_{k+1}) and computes only the columns >= b_k of them
+#     (sb2_sim_build_upper_dev: tiles at or above the block diagonal), with the b_k chosen so that every rank gets
+#     the same number of upper-triangular tiles -- 1/N of the single-GPU work.  The missing columns [0, b_k) are the
+#     transposes of sub-blocks computed by the ranks before k; one round of NCCL send / recv moves them (half the
+#     matrix in total, ~3 GB at the ml-20M shape, against ~1 s of tensor-core work).
+#   symmetric=False: every rank computes the whole rectangle of its rows (twice the work, no exchange).
+# Row blocks are multiples of the 256-row tile of the CTA-pair MMA kernel.
 # ------------------------------------------------------------------------------------------------------------
 def sim_row_range(n_x, rank, world, tile=256):
     """Contiguous, tile-aligned row range of `rank` (balanced in tiles)."""
@@ -162,21 +167,68 @@ def sim_row_range(n_x, rank, world, tile=256):
     return min(lo * tile, n_x), min(hi * tile, n_x)
 
 
-def sim_build_sharded(dist, kind, n_x, yr, min_support, gather=False, **kw):
+def sim_tri_ranges(n_x, world, tile=256):
+    """world contiguous tile-aligned row ranges with (nearly) equal numbers of upper-triangular tiles: row block rb
+    costs n_tiles - rb tiles.  Ranges may be empty when there are fewer row blocks than ranks."""
+    n_tiles = (n_x + tile - 1) // tile
+    total = n_tiles * (n_tiles + 1) // 2
+    bounds, acc, rb = [0], 0, 0
+    for k in range(1, world):
+        target = total * k / world
+        while rb < n_tiles and acc + (n_tiles - rb) / 2.0 <= target:
+            acc += n_tiles - rb
+            rb += 1
+        bounds.append(rb)
+    bounds.append(n_tiles)
+    return [(min(bounds[k] * tile, n_x), min(bounds[k + 1] * tile, n_x)) for k in range(world)]
+
+
+def sim_exchange_plan(ranges, rank):
+    """The transposed sub-blocks `rank` sends and receives in the symmetric build: lists of (peer, rows, cols) in
+    the coordinates of the full matrix.  Rank j < k sends sim[rows_j, rows_k]; rank k stores its transpose."""
+    lo, hi = ranges[rank]
+    sends = [(k, (lo, hi), ranges[k]) for k in range(rank + 1, len(ranges)) if hi > lo and ranges[k][1] > ranges[k][0]]
+    recvs = [(j, ranges[j], (lo, hi)) for j in range(rank) if hi > lo and ranges[j][1] > ranges[j][0]]
+    return sends, recvs
+
+
+def sim_exchange(dist, torch, block, ranges, rank):
+    """In place: fills the columns [0, row_begin) of `block` (rows ranges[rank] of the symmetric matrix, columns
+    >= row_begin already computed) with the transposes of the sub-blocks the earlier ranks computed."""
+    b, e = ranges[rank]
+    sends, recvs = sim_exchange_plan(ranges, rank)
+    ops, bufs = [], []
+    for peer, _, (c0, c1) in sends:
+        ops.append(dist.P2POp(dist.isend, block[:, c0:c1].contiguous(), peer))
+    for peer, (r0, r1), _ in recvs:
+        buf = torch.empty((r1 - r0, e - b), dtype=block.dtype, device=block.device)
+        bufs.append((buf, r0, r1))
+        ops.append(dist.P2POp(dist.irecv, buf, peer))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, r0, r1 in bufs:
+        block[:, r0:r1] = buf.t()
+
+
+def sim_build_sharded(dist, kind, n_x, yr, min_support, gather=False, symmetric=True, **kw):
     """Returns (row_begin, row_end, block) with block a CUDA float64 tensor (row_end-row_begin) x n_x; with
     gather=True every rank also receives the full matrix (all_gather over NCCL), returned instead of the block."""
     from . import similarities as sims
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
-    b, e = sim_row_range(n_x, rank, world)
+    symmetric = symmetric and world > 1
+    ranges = sim_tri_ranges(n_x, world) if symmetric else [sim_row_range(n_x, r, world) for r in range(world)]
+    b, e = ranges[rank]
     torch = sims.nat.torch_cuda()
     if e > b:
-        block = sims.build_device(kind, n_x, yr, min_support, row_begin=b, row_end=e, **kw)
+        block = sims.build_device(kind, n_x, yr, min_support, row_begin=b, row_end=e, upper=symmetric, **kw)
     else:
         block = torch.empty((0, n_x), dtype=torch.float64, device=sims.nat.device())
+    if symmetric:
+        sim_exchange(dist, torch, block, ranges, rank)
     if not gather or world == 1:
         return b, e, block
-    ranges = [sim_row_range(n_x, r, world) for r in range(world)]
     rows_max = max(hi - lo for lo, hi in ranges)
     pad = torch.zeros((rows_max, n_x), dtype=torch.float64, device=block.device)
     pad[:e - b] = block
@@ -211,11 +263,13 @@ def _all_gather_rows(dist, full, ranges, rank):
             full[a:b] = parts[r][:b - a]
 
 
-def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0):
+def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0, stats=None):
     """u, i, r: all_ratings COO (host arrays, identical on every rank); prm: _native.NmfParams; pu0 / qi0: the
     rng.uniform initial factors.  Returns (pu, qi, bu, bi) as float64 numpy arrays, identical on every rank and
-    bit-identical to the single-GPU fit."""
+    bit-identical to the single-GPU fit.  stats (dict, optional) receives 'epochs_s': the wall clock of the epoch
+    loop alone (device-synchronised, barrier on both sides), without upload / plan creation / download."""
     import ctypes as C
+    import time
     from . import _native as nat
     torch = nat.torch_cuda()
     rank = dist.get_rank() if dist is not None else 0
@@ -234,6 +288,11 @@ def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0):
     (u0, u1), (i0, i1) = ur[rank], ir[rank]
     try:
         cur = 0
+        if stats is not None:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
         for _ in range(prm.n_epochs):
             nat.check(lib.sb2_nmf_plan_epoch_dev(plan, C.byref(prm), nat.ptr(pu[cur]), nat.ptr(qi[cur]),
                                                  nat.ptr(pu[cur ^ 1]), nat.ptr(qi[cur ^ 1]), nat.ptr(bu), nat.ptr(bi),
@@ -243,6 +302,11 @@ def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0):
                 _all_gather_rows(dist, pu[cur], ur, rank)
                 _all_gather_rows(dist, qi[cur], ir, rank)
         nat.check(lib.sb2_nmf_plan_status(plan, nat.stream()))
+        if stats is not None:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            stats["epochs_s"] = time.perf_counter() - t0
     finally:
         lib.sb2_nmf_plan_destroy(plan)
     return pu[cur].cpu().numpy(), qi[cur].cpu().numpy(), bu.cpu().numpy(), bi.cpu().numpy()

@@ -53,29 +53,41 @@ def rating_denominator(r):
                      % (_DENOMS,))
 
 
-def build_device(kind, n_x, yr, min_support, global_mean=0.0, x_biases=None, y_biases=None, shrinkage=100,
-                 row_begin=0, row_end=None):
-    """Returns the (row_end-row_begin) x n_x similarity block as a CUDA float64 torch tensor."""
+def upload_inputs(kind, n_x, yr, x_biases=None, y_biases=None):
+    """Host-side preparation shared by every build on the same ratings: flatten yr, find the rating grid, copy the CSR
+    (and the baselines) to the device.  Returns a dict consumed by build_device(..., inputs=...)."""
     n_x = int(n_x)
-    row_end = n_x if row_end is None else int(row_end)
     ptr, idx, val = _flatten(yr, None if y_biases is None else len(y_biases))
     n_y = len(ptr) - 1
     denom = rating_denominator(val)
     if idx.size and (idx.min() < 0 or idx.max() >= n_x):
         raise IndexError("x index out of range for n_x=%d" % n_x)
-    d_ptr, d_idx, d_val = nat.to_dev(ptr, np.int64), nat.to_dev(idx, np.int32), nat.to_dev(val, np.float64)
-    d_bx = d_by = None
+    inp = dict(n_x=n_x, n_y=n_y, nnz=len(val), denom=denom, ptr=nat.to_dev(ptr, np.int64), idx=nat.to_dev(idx, np.int32),
+               val=nat.to_dev(val, np.float64), bx=None, by=None)
     if kind == "pearson_baseline":
         bx = np.ascontiguousarray(x_biases, dtype=np.float64)
         by = np.ascontiguousarray(y_biases, dtype=np.float64)
         if len(bx) < n_x or len(by) < n_y:
             raise IndexError("bias arrays are shorter than n_x / n_y")
-        d_bx, d_by = nat.to_dev(bx, np.float64), nat.to_dev(by, np.float64)
+        inp["bx"], inp["by"] = nat.to_dev(bx, np.float64), nat.to_dev(by, np.float64)
+    return inp
+
+
+def build_device(kind, n_x, yr, min_support, global_mean=0.0, x_biases=None, y_biases=None, shrinkage=100,
+                 row_begin=0, row_end=None, upper=False, inputs=None):
+    """Returns the (row_end-row_begin) x n_x similarity block as a CUDA float64 torch tensor.  upper=True: only the
+    columns >= row_begin are computed (shard of a symmetric multi-rank build), the others are zero.
+    inputs: the result of upload_inputs() for the same (kind, n_x, yr, biases), to skip the host-side preparation."""
+    inp = inputs if inputs is not None else upload_inputs(kind, n_x, yr, x_biases, y_biases)
+    n_x = inp["n_x"]
+    row_end = n_x if row_end is None else int(row_end)
     out = nat.empty_dev((row_end - row_begin, n_x), np.float64)
-    rc = nat.lib().sb2_sim_build_dev(nat.SIM_KINDS[kind], n_x, n_y, nat.ptr(d_ptr), nat.ptr(d_idx), nat.ptr(d_val),
-                                     len(val), denom, int(min_support), float(global_mean), nat.ptr(d_bx),
-                                     nat.ptr(d_by), float(shrinkage), int(row_begin), row_end, nat.ptr(out),
-                                     nat.stream())
+    if upper:
+        out.zero_()
+    fn = nat.lib().sb2_sim_build_upper_dev if upper else nat.lib().sb2_sim_build_dev
+    rc = fn(nat.SIM_KINDS[kind], n_x, inp["n_y"], nat.ptr(inp["ptr"]), nat.ptr(inp["idx"]), nat.ptr(inp["val"]),
+            inp["nnz"], inp["denom"], int(min_support), float(global_mean), nat.ptr(inp["bx"]), nat.ptr(inp["by"]),
+            float(shrinkage), int(row_begin), row_end, nat.ptr(out), nat.stream())
     nat.check(rc)
     return out
 

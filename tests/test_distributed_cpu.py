@@ -124,3 +124,51 @@ def test_even_ranges():
         rs = D.even_ranges(n, w)
         assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
         assert max(hi - lo for lo, hi in rs) - min(hi - lo for lo, hi in rs) <= 1
+
+
+def test_sim_tri_ranges_balance_and_exchange_plan():
+    """Symmetric sharded similarity build: tile-aligned contiguous ranges with equal upper-triangular tile counts;
+    every send has exactly one matching receive."""
+    for n_x, world in ((27000, 8), (27000, 2), (3706, 2), (1187, 3), (300, 4), (256, 2)):
+        rs = D.sim_tri_ranges(n_x, world)
+        assert len(rs) == world and rs[0][0] == 0 and rs[-1][1] == n_x
+        for (lo, hi), (lo2, _) in zip(rs, rs[1:]):
+            assert hi == lo2 and lo % 256 == 0 and lo <= hi
+        nt = (n_x + 255) // 256
+        cost = [sum(nt - rb for rb in range(lo // 256, (hi + 255) // 256)) for lo, hi in rs]
+        assert sum(cost) == nt * (nt + 1) // 2
+        if nt >= 8 * world:
+            assert max(cost) <= 1.1 * min(cost)
+        sends = {(k, peer, rows, cols) for k in range(world) for (peer, rows, cols) in D.sim_exchange_plan(rs, k)[0]}
+        recvs = {(peer, k, rows, cols) for k in range(world) for (peer, rows, cols) in D.sim_exchange_plan(rs, k)[1]}
+        assert sends == recvs
+
+
+def _sim_worker(rank, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=3)
+    n = 1187
+    rng = np.random.RandomState(1)
+    full = rng.rand(n, n)
+    full = (full + full.T) / 2
+    ranges = D.sim_tri_ranges(n, 3)
+    b, e = ranges[rank]
+    block = torch.from_numpy(full[b:e].copy())
+    block[:, :b] = 0.0                      # what sb2_sim_build_upper_dev leaves untouched
+    D.sim_exchange(dist, torch, block, ranges, rank)
+    np.save(os.path.join(out_dir, "s%d.npy" % rank), block.numpy())
+    dist.destroy_process_group()
+
+
+def test_sim_exchange_three_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_sim_worker, args=(port, str(tmp_path)), nprocs=3, join=True)
+    rng = np.random.RandomState(1)
+    full = rng.rand(1187, 1187)
+    full = (full + full.T) / 2
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), "s%d.npy" % r)) for r in range(3)], axis=0)
+    assert np.array_equal(got, full)

@@ -136,6 +136,30 @@ def test_float_ratings_similarities(floats):
             assert np.allclose(got, want, rtol=0, atol=PB_ATOL, equal_nan=True), (kind, o, np.abs(got - want).max())
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_sim_upper_shards_assemble_to_full(u1, kind):
+    """Symmetric multi-rank build emulated on one GPU: the upper-only shards of 3 ranks (sb2_sim_build_upper_dev),
+    completed by the transposes the NCCL exchange would deliver, equal the single-GPU matrix bit for bit."""
+    from surprise_b200 import distributed as D
+    ts, _ = u1
+    n_x, yr = ts.n_items, ts.user_csr()
+    kw = {}
+    if kind == "pearson_baseline":
+        algo = sb.BaselineOnly()
+        sb.AlgoBase.fit(algo, ts)
+        bu, bi = algo.compute_baselines()
+        kw = dict(global_mean=float(ts.global_mean), x_biases=bi, y_biases=bu)
+    want = sims.build_device(kind, n_x, yr, 1, **kw).cpu().numpy()
+    ranges = D.sim_tri_ranges(n_x, 3)
+    blocks = [sims.build_device(kind, n_x, yr, 1, row_begin=b, row_end=e, upper=True, **kw).cpu().numpy() for b, e in ranges]
+    for k, (b, e) in enumerate(ranges):
+        assert np.all(blocks[k][:, :b] == 0)            # untouched
+        for j in range(k):
+            bj, ej = ranges[j]
+            blocks[k][:, bj:ej] = blocks[j][:, b:e].T     # what sim_exchange delivers
+    assert np.array_equal(np.concatenate(blocks, axis=0), want, equal_nan=True)
+
+
 def test_similarity_errors():
     with pytest.raises(ZeroDivisionError):
         sims.msd(2, {0: [(0, 3.0)], 1: [(1, 4.0)]}, 0)
