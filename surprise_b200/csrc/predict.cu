@@ -70,15 +70,75 @@ int mf_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int f, i
 // ------------------------------------------------------------------------------------------------
 // k-NN.  One warp per (x, y) pair.
 //   neighbors = [(sim[x, x2], r) for (x2, r) in yr[y]]; heapq.nlargest(k, key=sim)
-// heapq.nlargest == sorted(reverse=True)[:k]: descending by sim, ties keep list order.  The warp
-// repeats k rounds of "smallest element after the previously selected one in the total order
-// (sim desc, position asc)" with a shuffle arg-max; the gathered sims live in shared memory when the
-// list fits, otherwise they are re-gathered from the sim row.  The weighted sums are accumulated by
-// every lane identically, in selection order, in round-to-nearest fp64 without contraction -- the
-// same sequence of operations as the reference, hence the same bits.
+// heapq.nlargest == sorted(reverse=True)[:k]: descending by sim, ties keep list order, i.e. the total order
+// (sim desc, position asc).  Selection:
+//   phase A  every lane walks its strided share of the list ONCE (index load + gathered sim) and keeps its own
+//            best KNN_L candidates, sorted, in registers -- one pass over the list instead of one per neighbour;
+//   phase B  up to k rounds: the best head of the 32 lane buffers is found with three warp reductions
+//            (redux.sync on the high / low word of an order-preserving integer image of sim, then on the
+//            position), the winning lane advances.  A lane whose buffer runs dry although it had to drop
+//            candidates re-walks its share for the next KNN_L after the last one it gave out (exact, rare).
+// The weighted sums are accumulated by every lane identically, in selection order, in round-to-nearest fp64
+// without contraction -- the same sequence of operations as the reference, hence the same bits.
 // ------------------------------------------------------------------------------------------------
 constexpr int KNN_WARPS = 8;
-constexpr int KNN_CACHE = 768;  // sims cached per warp (doubles)
+constexpr int KNN_L = 8;  // candidates kept per lane
+
+// order-preserving map double -> uint64 (larger = more similar); NaN -> 0 (never selected); -0.0 == +0.0
+__device__ __forceinline__ unsigned long long knn_key(double s) {
+    if (s != s) return 0ull;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(s + 0.0);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double knn_unkey(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+struct KnnBuf {
+    unsigned long long key[KNN_L];
+    int pos[KNN_L];
+    int cnt;       // valid entries
+    bool dropped;  // an eligible candidate did not fit: more may follow after the buffer's last entry
+};
+
+// lane-local: best KNN_L candidates strictly after (bound_key, bound_pos) in (key desc, pos asc) order
+__device__ __forceinline__ void knn_fill(KnnBuf& q, const double* __restrict__ srow, const int32_t* __restrict__ idx,
+                                         int64_t len, int lane, bool bounded, unsigned long long bound_key, int bound_pos) {
+    q.cnt = 0;
+    q.dropped = false;
+#pragma unroll
+    for (int t = 0; t < KNN_L; ++t) { q.key[t] = 0ull; q.pos[t] = 0x7FFFFFFF; }
+    for (int64_t a0 = lane; a0 < len; a0 += 4 * 32) {
+        double sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t a = a0 + 32 * u;
+            sv[u] = a < len ? srow[idx[a]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t a = a0 + 32 * u;
+            if (a >= len) break;
+            unsigned long long ck = knn_key(sv[u]);
+            int cp = (int)a;
+            if (ck == 0ull) continue;  // NaN
+            if (bounded && !(ck < bound_key || (ck == bound_key && cp > bound_pos))) continue;
+            // positions arrive in ascending order, so on equal keys the newcomer is worse: insert below equals
+            if (q.cnt == KNN_L && !(ck > q.key[KNN_L - 1])) { q.dropped = true; continue; }
+            if (q.cnt == KNN_L) q.dropped = true; else ++q.cnt;
+#pragma unroll
+            for (int t = 0; t < KNN_L; ++t) {
+                const bool better = ck > q.key[t] || (ck == q.key[t] && cp < q.pos[t]);
+                if (better) {
+                    const unsigned long long tk = q.key[t]; const int tp = q.pos[t];
+                    q.key[t] = ck; q.pos[t] = cp;
+                    ck = tk; cp = tp;
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t* __restrict__ y, int64_t n_x,
@@ -86,7 +146,9 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
                    const int32_t* __restrict__ x_idx, const double* __restrict__ r, int k, int min_k, int mode,
                    double mu, const double* __restrict__ bx, const double* __restrict__ by, double* __restrict__ est,
                    int32_t* __restrict__ actual_k, uint8_t* __restrict__ impossible) {
-    __shared__ double cache[KNN_WARPS][KNN_CACHE];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ unsigned long long bkey_s[KNN_WARPS][KNN_L][32];
+    __shared__ int bpos_s[KNN_WARPS][KNN_L][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int64_t p = blockIdx.x * (int64_t)KNN_WARPS + w; p < n_pairs; p += (int64_t)gridDim.x * KNN_WARPS) {
         const int32_t xx = x[p], yy = y[p];
@@ -106,51 +168,81 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
             if (mode >= 3) e = bx[xx];  // means[x] (knns.py:187, :382)
             const int64_t b = y_ptr[yy], len = y_ptr[yy + 1] - b;
             const double* srow = sim + (size_t)xx * (size_t)sim_ld;
-            const bool cached = len <= KNN_CACHE;
-            if (cached) {
-                for (int64_t a = lane; a < len; a += 32) cache[w][a] = srow[x_idx[b + a]];
-                __syncwarp();
-            }
-            double last_s = 0.0;
-            int64_t last_pos = -1;
-            bool first = true;
+            const int32_t* idx = x_idx + b;
+            KnnBuf q;
+            knn_fill(q, srow, idx, len, lane, false, 0ull, 0);
+            // the sorted lane buffers live in shared memory ([slot][lane]: conflict-free) so that the head is one
+            // indexed read per round instead of a select chain over registers (the kernel is issue-bound)
+#pragma unroll
+            for (int u = 0; u < KNN_L; ++u) { bkey_s[w][u][lane] = q.key[u]; bpos_s[w][u][lane] = q.pos[u]; }
+            int head = 0;
             double sum_sim = 0.0, sum_r = 0.0;
             ak = 0;
             const int64_t rounds = len < (int64_t)k ? len : (int64_t)k;
-            for (int64_t t = 0; t < rounds; ++t) {
-                // best candidate strictly after (last_s, last_pos) in (sim desc, pos asc) order
-                double bs = 0.0;
-                int64_t bp = -1;
-                for (int64_t a = lane; a < len; a += 32) {
-                    const double s = cached ? cache[w][a] : srow[x_idx[b + a]];
-                    const bool after = first || s < last_s || (s == last_s && a > last_pos);
-                    if (after && (bp < 0 || s > bs)) { bs = s; bp = a; }  // ascending a: first max wins
-                }
+            // Selection runs in batches of 32 rounds that touch only registers; lane j keeps the j-th winner of the
+            // batch.  The ratings (and neighbour baselines) of a batch are then gathered by all lanes at once and the
+            // two sums advance in selection order from lane 0 upwards -- one memory round trip per batch instead
+            // of one per neighbour in the dependent chain.
+            bool done = false;
+            for (int64_t t0 = 0; t0 < rounds && !done; t0 += 32) {
+                const int batch = (int)((rounds - t0) < 32 ? (rounds - t0) : 32);
+                int nb = 0;
+                double my_bs = 0.0;
+                int my_bp = 0;
+                for (int t = 0; t < batch; ++t) {
+                    // refill lanes that ran dry but had dropped candidates (the bound is the last entry they gave out)
+                    const bool dry = head == q.cnt && q.dropped;
+                    if (__any_sync(FULL, dry)) {
+                        if (dry) {
+                            const unsigned long long bk = bkey_s[w][KNN_L - 1][lane];
+                            const int bp = bpos_s[w][KNN_L - 1][lane];
+                            knn_fill(q, srow, idx, len, lane, true, bk, bp);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double os = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
-                    const int64_t op = __shfl_xor_sync(0xFFFFFFFFu, bp, o);
-                    if (op >= 0 && (bp < 0 || os > bs || (os == bs && op < bp))) { bs = os; bp = op; }
+                            for (int u = 0; u < KNN_L; ++u) { bkey_s[w][u][lane] = q.key[u]; bpos_s[w][u][lane] = q.pos[u]; }
+                            head = 0;
+                        }
+                        __syncwarp(FULL);
+                    }
+                    // head of this lane's buffer (entries are kept best-first)
+                    unsigned long long hk = 0ull;
+                    int hp = 0x7FFFFFFF;
+                    if (head < q.cnt) { hk = bkey_s[w][head][lane]; hp = bpos_s[w][head][lane]; }
+                    const unsigned hi = (unsigned)(hk >> 32);
+                    const unsigned m_hi = __reduce_max_sync(FULL, hi);
+                    bool alive = hi == m_hi && hk != 0ull;
+                    const unsigned lo = alive ? (unsigned)hk : 0u;
+                    const unsigned m_lo = __reduce_max_sync(FULL, lo);
+                    alive = alive && lo == m_lo;
+                    const unsigned long long bk = ((unsigned long long)m_hi << 32) | m_lo;
+                    if (bk == 0ull) { done = true; break; }  // nothing (or only NaNs) left
+                    const int bp = __reduce_min_sync(FULL, alive ? hp : 0x7FFFFFFF);
+                    const double bs = knn_unkey(bk);
+                    if (!(bs > 0.0)) { done = true; break; }  // everything that follows is <= 0 and contributes nothing
+                    if (alive && hp == bp) ++head;
+                    if (lane == nb) { my_bs = bs; my_bp = bp; }
+                    ++nb;
                 }
-                if (bp < 0) break;  // only NaNs left
-                first = false;
-                last_s = bs;
-                last_pos = bp;
-                if (!(bs > 0.0)) break;  // everything that follows is <= 0 and contributes nothing
-                const double rr = r[b + bp];
-                sum_sim = __dadd_rn(sum_sim, bs);
-                if (mode == 3) {
-                    sum_r = __dadd_rn(sum_r, __dmul_rn(bs, __dsub_rn(rr, bx[x_idx[b + bp]])));
-                } else if (mode == 4) {
-                    const int32_t nb = x_idx[b + bp];
-                    sum_r = __dadd_rn(sum_r, __ddiv_rn(__dmul_rn(bs, __dsub_rn(rr, bx[nb])), by[nb]));
-                } else if (mode != 0) {
-                    const double nb_bsl = __dadd_rn(__dadd_rn(mu, bx[x_idx[b + bp]]), by[yy]);
-                    sum_r = __dadd_rn(sum_r, __dmul_rn(bs, __dsub_rn(rr, nb_bsl)));
-                } else {
-                    sum_r = __dadd_rn(sum_r, __dmul_rn(bs, rr));
+                // per-neighbour term of the weighted sum, one neighbour per lane
+                double term = 0.0;
+                if (lane < nb) {
+                    const double rr = r[b + my_bp];
+                    if (mode == 0) {
+                        term = __dmul_rn(my_bs, rr);
+                    } else if (mode == 3) {
+                        term = __dmul_rn(my_bs, __dsub_rn(rr, bx[idx[my_bp]]));
+                    } else if (mode == 4) {
+                        const int32_t nbr = idx[my_bp];
+                        term = __ddiv_rn(__dmul_rn(my_bs, __dsub_rn(rr, bx[nbr])), by[nbr]);
+                    } else {
+                        const double nb_bsl = __dadd_rn(__dadd_rn(mu, bx[idx[my_bp]]), by[yy]);
+                        term = __dmul_rn(my_bs, __dsub_rn(rr, nb_bsl));
+                    }
                 }
-                ++ak;
+                for (int j = 0; j < nb; ++j) {
+                    sum_sim = __dadd_rn(sum_sim, __shfl_sync(FULL, my_bs, j));
+                    sum_r = __dadd_rn(sum_r, __shfl_sync(FULL, term, j));
+                }
+                ak += nb;
             }
             if (mode != 0) {
                 if (ak < min_k) sum_r = 0.0;
@@ -163,7 +255,6 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
                 else if (ak == 0) imp = 2;     // min_k <= 0: the reference divides 0 / 0
                 else e = __ddiv_rn(sum_r, sum_sim);
             }
-            __syncwarp();
         }
         if (lane == 0) {
             est[p] = e;

@@ -238,6 +238,45 @@ def sim_build_sharded(dist, kind, n_x, yr, min_support, gather=False, symmetric=
     return 0, n_x, full
 
 
+def knn_predict_sharded(dist, block, row_begin, row_end, n_x, x, y, yr, k, min_k, mode=0, global_mean=0.0, bx=None,
+                        by=None):
+    """Batched k-NN estimates with the similarity matrix left row-sharded (SURVEY.md 8e "KNN predict"): every rank
+    runs sb2_knn_predict_dev on the pairs whose x lies in its rows [row_begin, row_end) of `block`, the per-pair
+    results are summed across ranks (each pair is owned by exactly one rank; unknown x < 0 by rank 0).
+    x, y: int32 host arrays (identical on every rank); yr: (ptr, idx, val) host CSR.  Returns (est, actual_k,
+    impossible) numpy arrays in the order of the input pairs."""
+    from . import _native as nat
+    torch = nat.torch_cuda()
+    rank = dist.get_rank() if dist is not None else 0
+    x = np.ascontiguousarray(x, dtype=np.int32); y = np.ascontiguousarray(y, dtype=np.int32)
+    own = (x >= row_begin) & (x < row_end)
+    if rank == 0:
+        own |= x < 0
+    sel = np.nonzero(own)[0]
+    n = len(sel)
+    dev = block.device
+    est = torch.zeros(len(x), dtype=torch.float64, device=dev)
+    ak = torch.zeros(len(x), dtype=torch.int32, device=dev)
+    imp = torch.zeros(len(x), dtype=torch.int32, device=dev)
+    if n:
+        d_x, d_y = nat.to_dev(x[sel], np.int32), nat.to_dev(y[sel], np.int32)
+        d_ptr, d_idx, d_val = nat.to_dev(yr[0], np.int64), nat.to_dev(yr[1], np.int32), nat.to_dev(yr[2], np.float64)
+        d_bx = nat.to_dev(bx, np.float64) if bx is not None else None
+        d_by = nat.to_dev(by, np.float64) if by is not None else None
+        e_l = nat.empty_dev((n,), np.float64); a_l = nat.empty_dev((n,), np.int32); i_l = nat.empty_dev((n,), np.uint8)
+        # the kernel addresses sim + x * ld: shift the base so that global row ids index the local block
+        base = block.data_ptr() - int(row_begin) * int(n_x) * 8
+        nat.check(nat.lib().sb2_knn_predict_dev(n, nat.ptr(d_x), nat.ptr(d_y), n_x, base, n_x, nat.ptr(d_ptr), nat.ptr(d_idx),
+                                                nat.ptr(d_val), int(k), int(min_k), int(mode), float(global_mean),
+                                                nat.ptr(d_bx), nat.ptr(d_by), nat.ptr(e_l), nat.ptr(a_l), nat.ptr(i_l),
+                                                nat.stream()))
+        idx = torch.as_tensor(sel, device=dev)
+        est[idx] = e_l; ak[idx] = a_l; imp[idx] = i_l.to(torch.int32)
+    if dist is not None and dist.get_world_size() > 1:
+        dist.all_reduce(est); dist.all_reduce(ak); dist.all_reduce(imp)
+    return est.cpu().numpy(), ak.cpu().numpy(), imp.cpu().numpy().astype(np.uint8)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # NMF sharded over ranks, bit-exact (SURVEY.md section 8e, "bit-exact formulation"): rank g evaluates the ordered
 # accumulator sums of a contiguous range of users and a contiguous range of items (sb2_nmf_plan_epoch_dev) and

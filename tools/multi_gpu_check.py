@@ -28,6 +28,15 @@ for kind in ("cosine", "pearson"):
     torch.cuda.synchronize(); out[kind + "_sharded_s"] = time.perf_counter() - t0
     ref = sims.build_device(kind, ts.n_items, yr, 1)
     out[kind + "_bit_exact"] = bool(torch.equal(full, ref))
+# k-NN estimates with the matrix left sharded == single-GPU estimates on the full matrix
+rng = np.random.RandomState(5)
+px = rng.randint(-1, ts.n_items, 50000).astype(np.int32); py = rng.randint(0, ts.n_users, 50000).astype(np.int32)
+b, e, block = D.sim_build_sharded(dist if world > 1 else None, "msd", ts.n_items, yr, 1)
+got = D.knn_predict_sharded(dist if world > 1 else None, block, b, e, ts.n_items, px, py, yr, 40, 1)
+full = sims.build_device("msd", ts.n_items, yr, 1)
+ref = D.knn_predict_sharded(None, full, 0, ts.n_items, ts.n_items, px, py, yr, 40, 1)
+out["knn_sharded_bit_exact"] = bool(all(np.array_equal(a, c) for a, c in zip(got, ref)))
+del block, full
 # NMF sharded over ranks must be bit-identical to the single-GPU fit
 import ctypes as C
 from surprise_b200 import _native as nat
