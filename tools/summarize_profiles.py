@@ -41,8 +41,9 @@ def stalls(rep, title):
     if not os.path.exists(rep): return
     txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
-    hdr, data = rows[1], rows[2:]
+    hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
+    data = [r for r in rows[2:] if len(r) >= len(hdr) and r[ix['# Samples']].strip().isdigit()]
     st = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
     tot = sum(int(r[ix['# Samples']] or 0) for r in data)
     out.append('## %s: warp-stall samples (source page)\n' % title)
@@ -65,7 +66,38 @@ W = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 
 raw('svd_prof.ncu-rep', W, 'dsgd_svd_kernel, 20 epochs of the bench workload in one launch')
 stalls('svd_prof.ncu-rep', 'dsgd_svd_kernel')
 raw('gemm_prof.ncu-rep', W, 'gemm_u8_tc_kernel (tcgen05 kind::i8), cosine batch: 4 accumulators, 3+3 panels, 2080 tiles x 512 k-blocks')
-for f in ('sweep2.log', 'sweep3.log'):
-    pass
+stalls('gemm_prof.ncu-rep', 'gemm_u8_tc_kernel')
+W2 = W + ['l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+          'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct',
+          'lts__t_sector_hit_rate.pct', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active']
+raw('nmf_prof.ncu-rep', W2, 'nmf_pass_fused_kernel<16> (user pass), Netflix shape x0.6: 288000 users x 10620 items, 36M ratings, f=15')
+stalls('nmf_prof.ncu-rep', 'nmf_pass_fused_kernel')
+raw('knn_prof.ncu-rep', W2, 'knn_predict_kernel (capture of the register-select version; the committed kernel reads heads from shared memory), 2M pairs, k=40, ml-1M shape')
+stalls('knn_prof.ncu-rep', 'knn_predict_kernel')
+for src, dst in (('scale_n1.json', 'r1_scale_n1.json'), ('scale_n2.json', 'r1_scale_n2.json'), ('predict.json', 'r1_predict.json'),
+                 ('bench_ref.json', 'r1_bench_reference_arm.json')):
+    cp(src, dst)
+# DRAM traffic per launch of the dominant kernels, read by bench.py (roofline.traffic)
+def dram(rep):
+    rep = os.path.join(G, rep)
+    if not os.path.exists(rep): return None
+    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    tot = 0.0
+    for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+        i = hdr.index(name)
+        mul = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[units[i]]
+        tot += float(vals[i].replace(',', '')) * mul
+    return int(tot)
+traffic = {'source': 'ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum of one launch (tools/profile_svd.py, '
+                     'tools/profile_sim.py, tools/profile_nmf.py scale=0.6); see profiles/r1_summary.md'}
+for key, rep in (('dsgd_svd_kernel_dram_bytes_per_launch', 'svd_prof.ncu-rep'), ('gemm_u8_tc_kernel_dram_bytes_per_launch', 'gemm_prof.ncu-rep'),
+                 ('nmf_pass_fused_kernel_dram_bytes_per_launch_36M_ratings', 'nmf_prof.ncu-rep')):
+    v = dram(rep)
+    if v is not None: traffic[key] = v
+json.dump(traffic, open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
+notes = open(os.path.join(P, 'r1_notes.md')).read() if os.path.exists(os.path.join(P, 'r1_notes.md')) else ''
+out.append(notes)
 open(os.path.join(P, 'r1_summary.md'), 'w').write('# Round 1 profile summaries (B200, sm_100a)\n\nRaw artefacts next to this file: r1_*_launches.csv (ncu launch lists), r1_bench_n1.json / r1_bench_n2.json (bench lines of\nthe same build), r1_configs_full_shape.json (BASELINE.json configs 3-5 at full shape on one GPU), r1_dsgd_*.log\n(in-kernel phase counters, sb2_svd_plan_profile).\n\n' + '\n'.join(out))
 print('\n'.join(out)[:3000])
