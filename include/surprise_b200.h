@@ -285,6 +285,13 @@ int sb2_sim_build_upper_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y
                             const double* x_biases, const double* y_biases, double shrinkage, int64_t row_begin,
                             int64_t row_end, double* sim_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * rating_denom for sb2_sim_build*: the smallest d in {1, 2, 4, 5, 10, 20, 100, 1000} such that every rating
+ * (DEVICE array) is an integer multiple of 1/d within [0, 65535/d] (relative tolerance 1e-9, the same test
+ * sb2_sim_build applies); *denom_out (HOST int) = 0 when the ratings lie on none of these grids.
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_rating_denominator_dev(const double* r, int64_t nnz, int* denom_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

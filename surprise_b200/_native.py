@@ -83,6 +83,7 @@ SIGNATURES = {
                                _vp, _vp]),
     "sb2_slope_one_fit_dev": (_int, [_i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "sb2_slope_one_fit": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "sb2_rating_denominator_dev": (_int, [_vp, _i64, _vp, _vp]),
     "sb2_get_neighbors_dev": (_int, [_i64, _vp, _i64, _i64, _vp, _int, _vp, _vp]),
     "sb2_slope_one_predict_dev": (_int, [_i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -44,6 +44,7 @@ int sim_build_upper_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr
                         int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
                         const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
                         cudaStream_t st);
+int rating_denominator_dev(const double* r, int64_t nnz, int* denom_out, cudaStream_t st);
 int baseline_als_dev(int64_t n_users, int64_t n_items, const int64_t* u_ptr, const int32_t* ui_idx, const double* u_r,
                      const int64_t* i_ptr, const int32_t* iu_idx, const double* i_r, double mu, int n_epochs,
                      double reg_u, double reg_i, double* bu, double* bi, cudaStream_t st);
@@ -611,6 +612,15 @@ int sb2_sim_build_upper_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y
     SB2_TRY(ensure_device());
     return sim_build_upper_dev(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases,
                                y_biases, shrinkage, row_begin, row_end, sim_out, (cudaStream_t)stream);
+}
+
+int sb2_rating_denominator_dev(const double* r, int64_t nnz, int* denom_out, void* stream) {
+    SB2_TRY(ensure_device());
+    if (!denom_out) {
+        set_error("rating_denominator: null output");
+        return SB2_ERR_INVALID;
+    }
+    return rating_denominator_dev(r, nnz, denom_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

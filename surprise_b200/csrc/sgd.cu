@@ -189,6 +189,8 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
         for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
         const float err = BIASED ? r - (a.mu + b_u + b_i + dot) : r - dot;
         const float eg = err * isq;
+        const float dp = 1.f - a.lr_pu * a.reg_pu, dq = 1.f - a.lr_qi * a.reg_qi, dy = 1.f - a.lr_yj * a.reg_yj;
+        const float ep = a.lr_pu * err, eq = a.lr_qi * err, ey = a.lr_yj * err;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int ch = gl + c * G;
@@ -196,25 +198,26 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
             const float4 pz = p[c];  // p (+ z for SVD++)
             float4 po = pz;
             if (PP) { po.x -= z[c].x; po.y -= z[c].y; po.z -= z[c].z; po.w -= z[c].w; }
+            // p + lr (err q - reg p) = (1 - lr reg) p + (lr err) q: one multiply and one FMA per element
             float4 pn, qn;
-            pn.x = po.x + a.lr_pu * (err * q[c].x - a.reg_pu * po.x);
-            pn.y = po.y + a.lr_pu * (err * q[c].y - a.reg_pu * po.y);
-            pn.z = po.z + a.lr_pu * (err * q[c].z - a.reg_pu * po.z);
-            pn.w = po.w + a.lr_pu * (err * q[c].w - a.reg_pu * po.w);
-            qn.x = q[c].x + a.lr_qi * (err * pz.x - a.reg_qi * q[c].x);
-            qn.y = q[c].y + a.lr_qi * (err * pz.y - a.reg_qi * q[c].y);
-            qn.z = q[c].z + a.lr_qi * (err * pz.z - a.reg_qi * q[c].z);
-            qn.w = q[c].w + a.lr_qi * (err * pz.w - a.reg_qi * q[c].w);
+            pn.x = fmaf(ep, q[c].x, dp * po.x);
+            pn.y = fmaf(ep, q[c].y, dp * po.y);
+            pn.z = fmaf(ep, q[c].z, dp * po.z);
+            pn.w = fmaf(ep, q[c].w, dp * po.w);
+            qn.x = fmaf(eq, pz.x, dq * q[c].x);
+            qn.y = fmaf(eq, pz.y, dq * q[c].y);
+            qn.z = fmaf(eq, pz.z, dq * q[c].z);
+            qn.w = fmaf(eq, pz.w, dq * q[c].w);
             if (st) {
                 row_st4<SU>(prow + 4 * ch, pn);
                 row_st4<SI>(qrow + 4 * ch, qn);
             }
             if (PP) {
                 float4 zn, gn;
-                zn.x = z[c].x + a.lr_yj * (err * q[c].x - a.reg_yj * z[c].x);
-                zn.y = z[c].y + a.lr_yj * (err * q[c].y - a.reg_yj * z[c].y);
-                zn.z = z[c].z + a.lr_yj * (err * q[c].z - a.reg_yj * z[c].z);
-                zn.w = z[c].w + a.lr_yj * (err * q[c].w - a.reg_yj * z[c].w);
+                zn.x = fmaf(ey, q[c].x, dy * z[c].x);
+                zn.y = fmaf(ey, q[c].y, dy * z[c].y);
+                zn.z = fmaf(ey, q[c].z, dy * z[c].z);
+                zn.w = fmaf(ey, q[c].w, dy * z[c].w);
                 gn.x = g[c].x + eg * q[c].x; gn.y = g[c].y + eg * q[c].y;
                 gn.z = g[c].z + eg * q[c].z; gn.w = g[c].w + eg * q[c].w;
                 if (st) {

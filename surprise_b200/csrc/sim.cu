@@ -561,4 +561,30 @@ int slope_one_fit_dev(int64_t n_items, int64_t n_users, const int64_t* u_ptr, co
                     dev_out, freq_out, false, st);
 }
 
+// Smallest supported denominator d such that every rating is an integer multiple of 1/d in [0, 65535/d]
+// (1 stars, 2 half-stars, ..., 100 Jester's two decimals); 0 when the ratings are on none of the grids.
+// One pass of sim_analyze_kernel per candidate instead of several numpy passes over the ratings on the host.
+int rating_denominator_dev(const double* r, int64_t nnz, int* denom_out, cudaStream_t st) {
+    static const int cand[] = {1, 2, 4, 5, 10, 20, 100, 1000};
+    *denom_out = 1;
+    if (nnz <= 0) return SB2_OK;
+    DevBuf status_d;
+    SB2_TRY(status_d.alloc(ST_NWORDS * sizeof(int), st));
+    for (int d : cand) {
+        SB2_CUDA(cudaMemsetAsync(status_d.p, 0, ST_NWORDS * sizeof(int), st));
+        sim_analyze_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, st>>>(r, nnz, (double)d, 0, status_d.as<int>(), nullptr, 0,
+                                                                        0.0, nullptr, nullptr);
+        SB2_LAUNCH_CHECK();
+        int h[ST_NWORDS];
+        SB2_CUDA(cudaMemcpyAsync(h, status_d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        SB2_CUDA(cudaStreamSynchronize(st));
+        if (!h[ST_BAD_RATING]) {
+            *denom_out = d;
+            return SB2_OK;
+        }
+    }
+    *denom_out = 0;
+    return SB2_OK;
+}
+
 }  // namespace sb2

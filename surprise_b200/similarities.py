@@ -56,14 +56,20 @@ def rating_denominator(r):
 def upload_inputs(kind, n_x, yr, x_biases=None, y_biases=None):
     """Host-side preparation shared by every build on the same ratings: flatten yr, find the rating grid, copy the CSR
     (and the baselines) to the device.  Returns a dict consumed by build_device(..., inputs=...)."""
+    import ctypes as C
     n_x = int(n_x)
     ptr, idx, val = _flatten(yr, None if y_biases is None else len(y_biases))
     n_y = len(ptr) - 1
-    denom = rating_denominator(val)
-    if idx.size and (idx.min() < 0 or idx.max() >= n_x):
+    d_idx, d_val = nat.to_dev(idx, np.int32), nat.to_dev(val, np.float64)
+    # the checks that need a pass over the ratings run on the device copy (0.4 s of numpy at 20M ratings otherwise)
+    if len(val) and (int(d_idx.min()) < 0 or int(d_idx.max()) >= n_x):
         raise IndexError("x index out of range for n_x=%d" % n_x)
-    inp = dict(n_x=n_x, n_y=n_y, nnz=len(val), denom=denom, ptr=nat.to_dev(ptr, np.int64), idx=nat.to_dev(idx, np.int32),
-               val=nat.to_dev(val, np.float64), bx=None, by=None)
+    denom = C.c_int(1)
+    nat.check(nat.lib().sb2_rating_denominator_dev(nat.ptr(d_val), len(val), C.byref(denom), nat.stream()))
+    if denom.value == 0:
+        raise ValueError("similarity kernels need non-negative ratings on a 1/d grid, d in %s, with r*d <= 65535" % (_DENOMS,))
+    inp = dict(n_x=n_x, n_y=n_y, nnz=len(val), denom=denom.value, ptr=nat.to_dev(ptr, np.int64), idx=d_idx, val=d_val,
+               bx=None, by=None)
     if kind == "pearson_baseline":
         bx = np.ascontiguousarray(x_biases, dtype=np.float64)
         by = np.ascontiguousarray(y_biases, dtype=np.float64)
