@@ -172,3 +172,30 @@ def test_sim_exchange_three_ranks(tmp_path):
     full = (full + full.T) / 2
     got = np.concatenate([np.load(os.path.join(str(tmp_path), "s%d.npy" % r)) for r in range(3)], axis=0)
     assert np.array_equal(got, full)
+
+
+def _gather_worker(rank, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    n, f = 11, 3
+    truth = torch.arange(n * f, dtype=torch.float64).reshape(n, f)
+    ranges = D.even_ranges(n, 2)
+    lo, hi = ranges[rank]
+    full = torch.full((n, f), -1.0, dtype=torch.float64)
+    full[lo:hi] = truth[lo:hi]                     # what one NMF epoch leaves on this rank: only its own rows
+    D._all_gather_rows(dist, full, ranges, rank)
+    np.save(os.path.join(out_dir, "g%d.npy" % rank), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_nmf_all_gather_rows_two_ranks(tmp_path):
+    """The per-epoch exchange of the sharded NMF (uneven ranges): every rank ends up with every row."""
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_gather_worker, args=(port, str(tmp_path)), nprocs=2, join=True)
+    want = np.arange(33, dtype=np.float64).reshape(11, 3)
+    for r in range(2):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), "g%d.npy" % r)), want)
