@@ -13,17 +13,29 @@ SHAPES = {
 }
 
 
-def ratings(n_users, n_items, n_ratings, step=1.0, seed=0, holdout=0.1, rank=8):
+def ratings(n_users, n_items, n_ratings, step=1.0, seed=0, holdout=0.1, rank=8, skew=False):
     """Returns dict(train=(u, i, r), test=(u, i, r), n_users, n_items) with compact inner ids for the train
-    part (users / items that only occur in the test part get id -1 there = unknown)."""
+    part (users / items that only occur in the test part get id -1 there = unknown).
+    skew=True is the stress variant of SURVEY.md section 8d: Zipf(1.0) item popularity x log-normal user activity
+    (MovieLens-like: a few items rated by a large share of the users, a few very active users)."""
     rng = np.random.default_rng(seed)
     n_total = int(round(n_ratings * (1 + holdout)))
     if n_total > 0.5 * n_users * n_items:
         raise ValueError("shape too dense for the unique-pair sampler")
-    lin = np.unique(rng.integers(0, n_users * n_items, int(n_total * 1.08) + 16, dtype=np.int64))
+    if skew:
+        p_i = 1.0 / np.arange(1, n_items + 1)
+        p_i = rng.permutation(p_i / p_i.sum())
+        p_u = rng.lognormal(0.0, 1.0, n_users)
+        p_u /= p_u.sum()
+
+        def draw(k):
+            return rng.choice(n_users, k, p=p_u).astype(np.int64) * n_items + rng.choice(n_items, k, p=p_i)
+    else:
+        def draw(k):
+            return rng.integers(0, n_users * n_items, k, dtype=np.int64)
+    lin = np.unique(draw(int(n_total * 1.08) + 16))
     while len(lin) < n_total:
-        extra = rng.integers(0, n_users * n_items, n_total, dtype=np.int64)
-        lin = np.unique(np.concatenate((lin, extra)))
+        lin = np.unique(np.concatenate((lin, draw(n_total))))
     lin = rng.permutation(lin)[:n_total]
     u_raw = (lin // n_items).astype(np.int64)
     i_raw = (lin % n_items).astype(np.int64)

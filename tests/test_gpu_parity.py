@@ -642,3 +642,90 @@ def test_unknown_user_or_item_and_pickle(tmp_path):
         assert algo2.predict("user0", "item0", 4).est == q.est
     with pytest.raises(NameError):
         sb.KNNBasic(sim_options={"name": "wrong"}).fit(ts)
+
+
+# ---- stress variant of SURVEY 8d: Zipf item popularity x log-normal user activity ------------------------------------
+@pytest.fixture(scope="module")
+def skewed():
+    d = synth.ratings(3000, 1500, 150_000, seed=21, skew=True)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    assert np.bincount(i).max() > 1500 and np.bincount(u).max() > 300   # a 2000-rater item, 500-rating users
+    return d, ts
+
+
+def test_skewed_similarities_and_knn_bit_exact(skewed):
+    """Popular items / heavy users: long neighbour lists (beyond the per-lane buffers: refills) and large co-rating
+    counts, item-based; every similarity kind against the oracle's full matrix, k-NN estimates bit for bit."""
+    d, ts = skewed
+    yr = ts.user_csr()
+    n_x = ts.n_items
+    algo = sb.BaselineOnly()
+    sb.AlgoBase.fit(algo, ts)
+    bu, bi = algo.compute_baselines()
+    mu = float(ts.global_mean)
+    for kind in KINDS:
+        kw = dict(global_mean=mu, x_biases=bi, y_biases=bu) if kind == "pearson_baseline" else {}
+        got = sims.build_device(kind, n_x, yr, 1, **kw).cpu().numpy()
+        want = oracle.similarity(kind, n_x, *yr, 1, mu, bi, bu, 100.0)
+        if kind == "pearson_baseline":
+            assert np.allclose(got, want, rtol=0, atol=PB_ATOL, equal_nan=True), np.nanmax(np.abs(got - want))
+        else:
+            assert np.array_equal(got, want, equal_nan=True), kind
+    sim = oracle.similarity("msd", n_x, *yr, 1)
+    tu, ti, _ = d["test"]
+    x, y = np.asarray(ti, dtype=np.int32), np.asarray(tu, dtype=np.int32)
+    for (k, min_k, mode) in ((40, 1, 0), (300, 1, 0), (40, 1, 2)):
+        want = oracle.knn_estimate(x, y, sim, *yr, k, min_k, mode, mu, bi, bu)
+        est = np.empty(len(x)); ak = np.empty(len(x), dtype=np.int32); imp = np.empty(len(x), dtype=np.uint8)
+        nat.check(nat.lib().sb2_knn_predict(len(x), nat.hptr(x), nat.hptr(y), n_x, ts.n_users, nat.hptr(sim), nat.hptr(yr[0]),
+                                            nat.hptr(yr[1]), nat.hptr(yr[2]), k, min_k, mode, mu, nat.hptr(bi), nat.hptr(bu),
+                                            nat.hptr(est), nat.hptr(ak), nat.hptr(imp)))
+        ok = want[2] == 0
+        assert np.array_equal(imp, want[2]) and np.array_equal(ak[ok], want[1][ok]) and np.array_equal(est[ok], want[0][ok]), (k, mode)
+
+
+def test_skewed_nmf_bit_exact(skewed):
+    """Item segments of 2000+ entries next to segments of one entry."""
+    _, ts = skewed
+    uu, ii, rr = ts.coo()
+    f = 15
+    rng = np.random.RandomState(0)
+    pu0 = rng.uniform(0, 1, (ts.n_users, f)); qi0 = rng.uniform(0, 1, (ts.n_items, f))
+    want = oracle.nmf_sgd(ts.n_users, ts.n_items, uu, ii, rr, np.diff(ts.user_csr()[0]), np.diff(ts.item_csr()[0]), pu0, qi0, 4,
+                          False, 0.0, .06, .06, .02, .02, .005, .005)
+    pu, qi = pu0.copy(), qi0.copy()
+    bu, bi = np.empty(ts.n_users), np.empty(ts.n_items)
+    prm = nat.NmfParams(n_factors=f, n_epochs=4, biased=0, reserved=0, global_mean=0.0, reg_pu=.06, reg_qi=.06, reg_bu=.02,
+                        reg_bi=.02, lr_bu=.005, lr_bi=.005)
+    nat.check(nat.lib().sb2_nmf_fit(ts.n_users, ts.n_items, len(rr), nat.hptr(uu), nat.hptr(ii), nat.hptr(rr), C.byref(prm),
+                                    nat.hptr(pu), nat.hptr(qi), nat.hptr(bu), nat.hptr(bi)))
+    assert np.array_equal(pu, want[0]) and np.array_equal(qi, want[1])
+
+
+def test_skewed_svd_and_svdpp_rmse_vs_oracle(skewed):
+    """Cells with a 2000-rater item overflow the 63 colours (sequential tail); SVD++: y_j of a popular item decays
+    thousands of times per epoch.  Held-out RMSE / MAE within 0.005 of the sequential oracle."""
+    d, ts = skewed
+    uu, ii, rr = ts.coo()
+    ptr, idx, _ = ts.user_csr()
+    tu, ti, tr_ = d["test"]
+    mu = float(ts.global_mean)
+    rm = lambda e: float(np.sqrt(np.mean((np.clip(e, 1, 5) - tr_) ** 2)))
+    ma = lambda e: float(np.mean(np.abs(np.clip(e, 1, 5) - tr_)))
+    f = 20
+    rng = np.random.RandomState(0)
+    pu0 = rng.normal(0, .1, (ts.n_users, f)); qi0 = rng.normal(0, .1, (ts.n_items, f))
+    pu, qi, bu, bi = oracle.svd_sgd(uu, ii, rr, pu0, qi0, 10, True, mu, *([.005] * 4), *([.02] * 4))
+    want, _ = oracle.mf_estimate(tu, ti, True, mu, pu, qi, bu, bi)
+    algo = sb.SVD(n_factors=f, n_epochs=10, random_state=0).fit(ts)
+    got, _ = oracle.mf_estimate(tu, ti, True, mu, algo.pu, algo.qi, algo.bu, algo.bi)
+    assert abs(rm(want) - rm(got)) <= RMSE_TOL and abs(ma(want) - ma(got)) <= RMSE_TOL, ("svd", rm(want), rm(got))
+    rng = np.random.RandomState(0)
+    pu0 = rng.normal(0, .1, (ts.n_users, f)); qi0 = rng.normal(0, .1, (ts.n_items, f)); yj0 = rng.normal(0, .1, (ts.n_items, f))
+    pu, qi, yj, bu, bi = oracle.svdpp_sgd(uu, ii, rr, ptr, idx, pu0, qi0, yj0, 10, mu, *([.007] * 5), *([.02] * 5))
+    want, _ = oracle.mf_estimate(tu, ti, True, mu, pu, qi, bu, bi, yj, ptr, idx)
+    algo = sb.SVDpp(n_epochs=10, random_state=0).fit(ts)
+    got, _ = oracle.mf_estimate(tu, ti, True, mu, algo.pu, algo.qi, algo.bu, algo.bi, algo.yj, ptr, idx)
+    assert abs(rm(want) - rm(got)) <= RMSE_TOL and abs(ma(want) - ma(got)) <= RMSE_TOL, ("svdpp", rm(want), rm(got))
+
