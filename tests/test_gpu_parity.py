@@ -160,6 +160,20 @@ def test_sim_upper_shards_assemble_to_full(u1, kind):
     assert np.array_equal(np.concatenate(blocks, axis=0), want, equal_nan=True)
 
 
+def test_rating_denominator_on_device():
+    """sb2_rating_denominator_dev == similarities.rating_denominator (host) on every supported grid."""
+    rng = np.random.RandomState(0)
+    for d in (1, 2, 4, 5, 10, 20, 100, 1000):
+        r = rng.randint(0, 5 * d + 1, 5000) / d
+        r[0] = 1.0 / d                                  # make sure the finest step is present
+        got = C.c_int(-1)
+        nat.check(nat.lib().sb2_rating_denominator_dev(nat.ptr(nat.to_dev(r, np.float64)), len(r), C.byref(got), nat.stream()))
+        assert got.value == sims.rating_denominator(r) == d
+    got = C.c_int(-1)
+    nat.check(nat.lib().sb2_rating_denominator_dev(nat.ptr(nat.to_dev(np.array([np.pi, 2.0]), np.float64)), 2, C.byref(got), nat.stream()))
+    assert got.value == 0
+
+
 def test_similarity_errors():
     with pytest.raises(ZeroDivisionError):
         sims.msd(2, {0: [(0, 3.0)], 1: [(1, 4.0)]}, 0)
