@@ -527,6 +527,59 @@ def test_synthetic_svd_rmse_vs_oracle(f):
     assert abs(rm_w - rm_g) <= RMSE_TOL and abs(ma_w - ma_g) <= RMSE_TOL, (rm_w, rm_g)
 
 
+@pytest.mark.parametrize("f", (3, 50, 150, 300))
+def test_svd_lane_shapes_rmse_vs_oracle(f):
+    """Every (lanes, chunks-per-lane) shape of the update: f=3 -> 1 lane x 1 chunk, 50 -> 4 x 4, 150 -> 16 x 3 (512-thread
+    CTAs), 300 -> 32 lanes striding the row.  Held-out RMSE within 0.005 of the sequential oracle, and one epoch on a
+    conflict-free input equal to the oracle to fp32 rounding."""
+    d = synth.ratings(1500, 900, 60_000, seed=30 + f)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    uu, ii, rr = ts.coo()
+    tu, ti, tr_ = d["test"]
+    mu = float(ts.global_mean)
+    algo = sb.SVD(n_factors=f, n_epochs=6, random_state=3).fit(ts)
+    rng = np.random.RandomState(3)
+    pu0 = rng.normal(0, .1, (ts.n_users, f)); qi0 = rng.normal(0, .1, (ts.n_items, f))
+    pu, qi, bu, bi = oracle.svd_sgd(uu, ii, rr, pu0, qi0, 6, True, mu, *([.005] * 4), *([.02] * 4))
+    want, _ = oracle.mf_estimate(tu, ti, True, mu, pu, qi, bu, bi)
+    got, _ = oracle.mf_estimate(tu, ti, True, mu, algo.pu, algo.qi, algo.bu, algo.bi)
+    rm = lambda e: float(np.sqrt(np.mean((np.clip(e, 1, 5) - tr_) ** 2)))
+    assert abs(rm(want) - rm(got)) <= RMSE_TOL, (f, rm(want), rm(got))
+    n = 400
+    rs = np.random.RandomState(2)
+    pu_, pi_ = np.arange(n, dtype=np.int32), rs.permutation(n).astype(np.int32)
+    pr_ = rs.randint(1, 6, n).astype(np.float64)
+    tsp = sb.Trainset.from_coo(pu_, pi_, pr_, n, n)
+    a2 = sb.SVD(n_factors=f, n_epochs=2, random_state=4).fit(tsp)
+    rs = np.random.RandomState(4)
+    p0 = rs.normal(0, .1, (n, f)); q0 = rs.normal(0, .1, (n, f))
+    p1, q1, b1, c1 = oracle.svd_sgd(pu_, pi_, pr_, p0, q0, 2, True, float(tsp.global_mean), *([.005] * 4), *([.02] * 4))
+    assert np.allclose(a2.pu, p1, rtol=0, atol=3e-6) and np.allclose(a2.qi, q1, rtol=0, atol=3e-6)
+    assert np.allclose(a2.bu, b1, rtol=0, atol=3e-6) and np.allclose(a2.bi, c1, rtol=0, atol=3e-6)
+
+
+@pytest.mark.parametrize("f", (40, 150))
+def test_svdpp_wide_factors_rmse_vs_oracle(f):
+    """SVD++ user rows are [p | z | g] = 3 x the factor row: f=40 -> 4 lanes x 3 chunks, f=150 -> 16 x 3 with user rows
+    too long to stage every block in shared memory."""
+    d = synth.ratings(800, 500, 25_000, seed=40 + f)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
+    uu, ii, rr = ts.coo()
+    ptr, idx, _ = ts.user_csr()
+    tu, ti, tr_ = d["test"]
+    mu = float(ts.global_mean)
+    algo = sb.SVDpp(n_factors=f, n_epochs=5, random_state=0).fit(ts)
+    rng = np.random.RandomState(0)
+    pu0 = rng.normal(0, .1, (ts.n_users, f)); qi0 = rng.normal(0, .1, (ts.n_items, f)); yj0 = rng.normal(0, .1, (ts.n_items, f))
+    pu, qi, yj, bu, bi = oracle.svdpp_sgd(uu, ii, rr, ptr, idx, pu0, qi0, yj0, 5, mu, *([.007] * 5), *([.02] * 5))
+    want, _ = oracle.mf_estimate(tu, ti, True, mu, pu, qi, bu, bi, yj, ptr, idx)
+    got, _ = oracle.mf_estimate(tu, ti, True, mu, algo.pu, algo.qi, algo.bu, algo.bi, algo.yj, ptr, idx)
+    rm = lambda e: float(np.sqrt(np.mean((np.clip(e, 1, 5) - tr_) ** 2)))
+    assert abs(rm(want) - rm(got)) <= RMSE_TOL, (f, rm(want), rm(got))
+
+
 def test_svd_conflict_free_input_matches_oracle():
     """A permutation matrix of ratings (no two share a user or an item) makes SGD order-independent:
     the stratified kernel must then reproduce the sequential oracle up to fp32 rounding."""
