@@ -123,8 +123,9 @@ __global__ void sim_pack_kernel(const PackArgs p) {
 struct FinArgs {
     int kind;
     int64_t n_x, ld;           // planes: rows x ld
-    int64_t row_begin, row_end;  // global rows covered
-    int64_t plane_row0;
+    int64_t row_begin, row_end;  // global rows covered by this build (output rows are relative to row_begin)
+    int64_t band_begin, band_end;  // rows finalized by this launch (their planes are resident)
+    int64_t plane_row0;          // global row of plane row 0
     const double* freq;
     const double* prods;
     const double* sqi;
@@ -139,8 +140,6 @@ struct FinArgs {
     double a_shift;
     double inv_d, inv_d2;  // 1/denom, 1/denom^2
     int min_support;
-    int upper;    // row shard computes only columns >= row_begin (tiles at or above the block diagonal)
-    int tile_rows;
     double shrinkage;
     double* sim;  // (row_end-row_begin) x n_x
     int* status;
@@ -197,20 +196,23 @@ __device__ __forceinline__ double sim_value(const FinArgs& f, size_t o, int64_t 
     return s;
 }
 
-// symmetric build: 32x32 tiles with tj >= ti; the tile's values go to sim[i][j] and (transposed
-// through shared memory) to sim[j][i], exactly like the reference mirrors (similarities.pyx:95).
+// symmetric build: 32x32 tiles with tj >= ti; the tile's values go to sim[i][j] and (transposed through shared
+// memory) to sim[j][i], exactly like the reference mirrors (similarities.pyx:95).  Rows [f.band_begin, f.band_end)
+// of the matrix are finalized per launch (their planes are resident); output rows are relative to f.row_begin
+// (0 for the single-GPU build, the shard's first row for an upper-only shard), and the mirror is written only
+// when the column is itself a row this build owns (j < f.row_end).
 __global__ void sim_finalize_sym_kernel(const FinArgs f) {
     __shared__ double tile[32][33];
-    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int ti = (int)(f.band_begin / 32) + blockIdx.y, tj = blockIdx.x;
     if (tj < ti) return;
     const int tx = threadIdx.x, ty0 = threadIdx.y;  // block 32 x 8
     for (int ty = ty0; ty < 32; ty += 8) {
         const int64_t i = (int64_t)ti * 32 + ty, j = (int64_t)tj * 32 + tx;
         double s = 0.0;
-        if (i < f.n_x && j < f.n_x) {
+        if (i < f.band_end && j < f.n_x) {
             if (i == j) s = 1.0;
-            else if (i < j) s = sim_value(f, (size_t)i * f.ld + j, i, j, false);
-            if (i <= j) f.sim[(size_t)i * f.n_x + j] = s;
+            else if (i < j) s = sim_value(f, (size_t)(i - f.plane_row0) * f.ld + j, i, j, false);
+            if (i <= j) f.sim[(size_t)(i - f.row_begin) * f.n_x + j] = s;
         }
         tile[ty][tx] = s;
     }
@@ -218,21 +220,17 @@ __global__ void sim_finalize_sym_kernel(const FinArgs f) {
     for (int ty = ty0; ty < 32; ty += 8) {
         // element (row = tj*32+ty, col = ti*32+tx) = value at (col, row)
         const int64_t i = (int64_t)tj * 32 + ty, j = (int64_t)ti * 32 + tx;
-        if (i < f.n_x && j < f.n_x && j < i) f.sim[(size_t)i * f.n_x + j] = tile[tx][ty];
+        if (i < f.row_end && j < f.band_end && j < i) f.sim[(size_t)(i - f.row_begin) * f.n_x + j] = tile[tx][ty];
     }
 }
 
 // row-shard build: every (i, j) of the shard rows, accumulators valid at (i, j) itself
 __global__ void sim_finalize_rows_kernel(const FinArgs f) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t i = f.row_begin + blockIdx.y;
-    if (j >= f.n_x || i >= f.row_end) return;
+    const int64_t i = f.band_begin + blockIdx.y;
+    if (j >= f.n_x || i >= f.band_end) return;
     double s;
-    if (f.upper && j < f.row_begin) return;  // owned (transposed) by an earlier shard, filled in by the exchange
     if (i == j) s = 1.0;
-    else if (f.upper && j < i && j / f.tile_rows < i / f.tile_rows)
-        // below the block diagonal: the tile was not computed; its mirror (j, i) lies in this shard's planes
-        s = sim_value(f, (size_t)(j - f.plane_row0) * f.ld + i, j, i, false);
     else s = sim_value(f, (size_t)(i - f.plane_row0) * f.ld + j, i, j, i > j);
     f.sim[(size_t)(i - f.row_begin) * f.n_x + j] = s;
 }
@@ -245,14 +243,14 @@ __global__ void sim_finalize_rows_kernel(const FinArgs f) {
 __global__ void slope_finalize_kernel(const FinArgs f, int64_t* __restrict__ freq_out, double* __restrict__ dev_out) {
     __shared__ double tdev[32][33];
     __shared__ double tfreq[32][33];
-    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int ti = (int)(f.band_begin / 32) + blockIdx.y, tj = blockIdx.x;
     if (tj < ti) return;
     const int tx = threadIdx.x, ty0 = threadIdx.y;
     for (int ty = ty0; ty < 32; ty += 8) {
         const int64_t i = (int64_t)ti * 32 + ty, j = (int64_t)tj * 32 + tx;
         double d = 0.0, n = 0.0;
-        if (i < f.n_x && j < f.n_x && i <= j) {
-            const size_t o = (size_t)i * f.ld + j;
+        if (i < f.band_end && j < f.n_x && i <= j) {
+            const size_t o = (size_t)(i - f.plane_row0) * f.ld + j;
             n = f.freq[o];
             if (i < j) d = __ddiv_rn(__dsub_rn(f.si[o], f.sj[o]), n);
             freq_out[(size_t)i * f.n_x + j] = (int64_t)n;
@@ -264,7 +262,7 @@ __global__ void slope_finalize_kernel(const FinArgs f, int64_t* __restrict__ fre
     __syncthreads();
     for (int ty = ty0; ty < 32; ty += 8) {
         const int64_t i = (int64_t)tj * 32 + ty, j = (int64_t)ti * 32 + tx;
-        if (i < f.n_x && j < f.n_x && j < i) {
+        if (i < f.n_x && j < f.band_end && j < i) {
             freq_out[(size_t)i * f.n_x + j] = (int64_t)tfreq[tx][ty];
             dev_out[(size_t)i * f.n_x + j] = -tdev[tx][ty];
         }
@@ -393,32 +391,29 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
         SB2_LAUNCH_CHECK();
     }
 
-    // ---- tile list ----------------------------------------------------------------------------
-    // Row blocks are walked in bands of 12; inside a band tiles go column-block-major, so the ~148
-    // tiles in flight share ~12 A-side and ~12 B-side row blocks of every panel (L2 reuse).
-    std::vector<int2> tiles;
-    {
-        const int rb0 = (int)(row_begin / TR), rb1 = (int)ceil_div(row_end, TR);
-        const int ncb = (int)(n_pad / TR);
-        const int band = TR == 256 ? 8 : 12;
-        for (int b0 = rb0; b0 < rb1; b0 += band)
-            for (int cb = 0; cb < ncb; ++cb)
-                for (int rb = b0; rb < std::min(b0 + band, rb1); ++rb)
-                    if ((!full && !upper) || cb >= rb) tiles.push_back(make_int2(rb, cb));
-    }
-    DevBuf tiles_d;
-    SB2_TRY(tiles_d.alloc(tiles.size() * sizeof(int2) + 16, st));
-    SB2_CUDA(cudaMemcpyAsync(tiles_d.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-
     // ---- planes + jobs ------------------------------------------------------------------------
     enum { P_FREQ, P_PRODS, P_SQI, P_SQJ, P_SI, P_SJ, P_T1IJ, P_T1JI, P_T2, P_A1, P_COUNT };
     bool need[P_COUNT] = {true, !slope, !slope, !slope, false, false, false, false, false, false};
     if (kind == SB2_SIM_PEARSON || pb || slope) need[P_SI] = need[P_SJ] = true;
     if (pb) need[P_T1IJ] = need[P_T1JI] = need[P_T2] = need[P_A1] = true;
-    const size_t plane_elems = (size_t)rows_pad * (size_t)ld;
     int n_planes = 0;
     int plane_slot[P_COUNT];
     for (int k = 0; k < P_COUNT; ++k) plane_slot[k] = need[k] ? n_planes++ : -1;
+    // The fp64 planes cover one BAND of row blocks at a time (GEMMs, then finalize, band after band), so their
+    // footprint is bounded (default 24 GiB; SB2_SIM_PLANE_GIB / SB2_SIM_BAND_ROWS override) instead of growing with
+    // rows x n_x x 10: at the ml-20M item-item shape 59 GB of planes become 24, and a 47k-row shard of a 138k x 138k
+    // user-user build (52 GB of output) still fits one 180 GB GPU.
+    const int rb0 = (int)(row_begin / TR), rb1 = (int)ceil_div(row_end, TR);
+    int band_rb = rb1 - rb0;
+    {
+        double gib = 24.0;
+        if (const char* e = getenv("SB2_SIM_PLANE_GIB")) gib = std::max(0.001, atof(e));
+        const double per_rb = (double)n_planes * (double)ld * 8.0 * TR;
+        band_rb = (int)std::max(1.0, std::min((double)band_rb, floor(gib * 1073741824.0 / per_rb)));
+        if (const char* e = getenv("SB2_SIM_BAND_ROWS")) band_rb = std::max(1, std::min(rb1 - rb0, atoi(e) / TR));
+        if (band_rb >= 8 && band_rb < rb1 - rb0) band_rb -= band_rb % 8;  // keep the 8-row-block L2 groups intact
+    }
+    const size_t plane_elems = (size_t)std::min<int64_t>(rows_pad, (int64_t)band_rb * TR) * (size_t)ld;
     DevBuf planes_d;
     SB2_TRY(planes_d.alloc(plane_elems * sizeof(double) * n_planes, st));
     auto plane = [&](int k) -> double* {
@@ -468,25 +463,31 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
         cudaEventCreate(&ev1);
         cudaEventRecord(ev0, st);
     }
-    if (!tiles.empty())
-        SB2_TRY(gemm_u8_tc_run(jobs.data(), (int)jobs.size(), n_pad, k_pad, tiles_d.as<int2>(), (int)tiles.size(), ld,
-                               row_begin, st));
-    if (timing) {
-        cudaEventRecord(ev1, st);
-        cudaEventSynchronize(ev1);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ev0, ev1);
-        const double ops = 2.0 * (double)jobs.size() * (double)tiles.size() * TR * TR * (double)k_pad;
-        fprintf(stderr, "[sb2] sim gemm: %d accumulators x %zu tiles x k=%lld: %.3f ms, %.1f TOP/s issued\n",
-                (int)jobs.size(), tiles.size(), (long long)k_pad, ms, ops / (ms * 1e-3) / 1e12);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
+    // ---- tile list: all bands, one upload ------------------------------------------------------
+    // Inside a band of planes, row blocks are walked in groups of 8 and tiles go column-block-major, so the ~148
+    // tiles in flight share ~8 A-side and ~8 B-side row blocks of every panel (L2 reuse).
+    std::vector<int2> tiles;
+    std::vector<size_t> band_off;
+    {
+        const int ncb = (int)(n_pad / TR);
+        const int grp = TR == 256 ? 8 : 12;
+        for (int p0 = rb0; p0 < rb1; p0 += band_rb) {
+            band_off.push_back(tiles.size());
+            const int p1 = std::min(p0 + band_rb, rb1);
+            for (int b0 = p0; b0 < p1; b0 += grp)
+                for (int cb = 0; cb < ncb; ++cb)
+                    for (int rb = b0; rb < std::min(b0 + grp, p1); ++rb)
+                        if ((!full && !upper) || cb >= rb) tiles.push_back(make_int2(rb, cb));
+        }
+        band_off.push_back(tiles.size());
     }
+    DevBuf tiles_d;
+    SB2_TRY(tiles_d.alloc(tiles.size() * sizeof(int2) + 16, st));
+    SB2_CUDA(cudaMemcpyAsync(tiles_d.p, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
 
-    // ---- finalize -----------------------------------------------------------------------------
     FinArgs f;
     memset(&f, 0, sizeof(f));
-    f.kind = kind; f.n_x = n_x; f.ld = ld; f.row_begin = row_begin; f.row_end = row_end; f.plane_row0 = row_begin;
+    f.kind = kind; f.n_x = n_x; f.ld = ld; f.row_begin = row_begin; f.row_end = row_end;
     f.freq = plane(P_FREQ); f.prods = plane(P_PRODS); f.sqi = plane(P_SQI); f.sqj = plane(P_SQJ);
     f.si = plane(P_SI); f.sj = plane(P_SJ); f.t1ij = plane(P_T1IJ); f.t1ji = plane(P_T1JI);
     f.t2 = plane(P_T2); f.a1 = plane(P_A1);
@@ -494,17 +495,33 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
     f.inv_d = 1.0 / (double)rating_denom;
     f.inv_d2 = 1.0 / ((double)rating_denom * (double)rating_denom);
     f.min_support = min_support; f.shrinkage = shrinkage; f.sim = sim_out; f.status = status_d.as<int>();
-    f.upper = (upper && !full) ? 1 : 0; f.tile_rows = TR;
-    if (slope) {
-        const unsigned nt = (unsigned)ceil_div(n_x, 32);
-        slope_finalize_kernel<<<dim3(nt, nt), dim3(32, 8), 0, st>>>(f, freq_out, sim_out);
-    } else if (full) {
-        const unsigned nt = (unsigned)ceil_div(n_x, 32);
-        sim_finalize_sym_kernel<<<dim3(nt, nt), dim3(32, 8), 0, st>>>(f);
-    } else {
-        sim_finalize_rows_kernel<<<dim3((unsigned)ceil_div(n_x, 256), (unsigned)(row_end - row_begin)), 256, 0, st>>>(f);
+    const unsigned nt = (unsigned)ceil_div(n_x, 32);
+    for (size_t bi = 0; bi + 1 < band_off.size(); ++bi) {
+        const int64_t band_begin = ((int64_t)rb0 + (int64_t)bi * band_rb) * TR;
+        const int64_t band_end = std::min<int64_t>(row_end, band_begin + (int64_t)band_rb * TR);
+        const size_t t0 = band_off[bi], nt_band = band_off[bi + 1] - t0;
+        if (nt_band)
+            SB2_TRY(gemm_u8_tc_run(jobs.data(), (int)jobs.size(), n_pad, k_pad, tiles_d.as<int2>() + t0, (int)nt_band, ld,
+                                   band_begin, st));
+        f.band_begin = band_begin; f.band_end = band_end; f.plane_row0 = band_begin;
+        const unsigned rows32 = (unsigned)ceil_div(band_end - band_begin, 32);
+        if (slope) slope_finalize_kernel<<<dim3(nt, rows32), dim3(32, 8), 0, st>>>(f, freq_out, sim_out);
+        else if (full || upper) sim_finalize_sym_kernel<<<dim3(nt, rows32), dim3(32, 8), 0, st>>>(f);
+        else sim_finalize_rows_kernel<<<dim3((unsigned)ceil_div(n_x, 256), (unsigned)(band_end - band_begin)), 256, 0, st>>>(f);
+        SB2_LAUNCH_CHECK();
     }
-    SB2_LAUNCH_CHECK();
+    if (timing) {
+        cudaEventRecord(ev1, st);
+        cudaEventSynchronize(ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        const double ops = 2.0 * (double)jobs.size() * (double)tiles.size() * TR * TR * (double)k_pad;
+        fprintf(stderr, "[sb2] sim gemm + finalize: %d accumulators x %zu tiles x k=%lld in %d band(s): %.3f ms, %.1f TOP/s issued\n",
+                (int)jobs.size(), tiles.size(), (long long)k_pad, (int)ceil_div(rb1 - rb0, band_rb), ms,
+                ops / (ms * 1e-3) / 1e12);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
 
     SB2_CUDA(cudaMemcpyAsync(status_h, status_d.p, sizeof(status_h), cudaMemcpyDeviceToHost, st));
     SB2_CUDA(cudaStreamSynchronize(st));

@@ -174,6 +174,36 @@ def test_rating_denominator_on_device():
     assert got.value == 0
 
 
+@pytest.mark.parametrize("band_rows", (256, 512))
+def test_sim_banded_planes_bit_identical(u1, monkeypatch, band_rows):
+    """The fp64 accumulator planes cover one band of row blocks at a time (bounded footprint); forcing 3 / 5 bands on
+    the 1187-item fixture must not change one bit of any matrix: single-GPU symmetric build, plain row shard,
+    upper-only shard, SlopeOne."""
+    from surprise_b200 import distributed as D
+    ts, _ = u1
+    n_x, yr = ts.n_items, ts.user_csr()
+    algo = sb.BaselineOnly()
+    sb.AlgoBase.fit(algo, ts)
+    bu, bi = algo.compute_baselines()
+
+    def build_all():
+        out = []
+        for kind in KINDS:
+            kw = dict(global_mean=float(ts.global_mean), x_biases=bi, y_biases=bu) if kind == "pearson_baseline" else {}
+            out.append(sims.build_device(kind, n_x, yr, 1, **kw).cpu().numpy())
+            out.append(sims.build_device(kind, n_x, yr, 1, row_begin=256, row_end=1100, **kw).cpu().numpy())
+            out.append(sims.build_device(kind, n_x, yr, 1, row_begin=256, row_end=n_x, upper=True, **kw).cpu().numpy())
+        so = sb.SlopeOne().fit(ts)
+        out += [so.freq.astype(np.float64), np.nan_to_num(so.dev, nan=123.0)]
+        return out
+    monkeypatch.delenv("SB2_SIM_BAND_ROWS", raising=False)
+    want = build_all()
+    monkeypatch.setenv("SB2_SIM_BAND_ROWS", str(band_rows))
+    got = build_all()
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b, equal_nan=True), k
+
+
 def test_similarity_errors():
     with pytest.raises(ZeroDivisionError):
         sims.msd(2, {0: [(0, 3.0)], 1: [(1, 4.0)]}, 0)
