@@ -400,13 +400,14 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
     int plane_slot[P_COUNT];
     for (int k = 0; k < P_COUNT; ++k) plane_slot[k] = need[k] ? n_planes++ : -1;
     // The fp64 planes cover one BAND of row blocks at a time (GEMMs, then finalize, band after band), so their
-    // footprint is bounded (default 24 GiB; SB2_SIM_PLANE_GIB / SB2_SIM_BAND_ROWS override) instead of growing with
-    // rows x n_x x 10: at the ml-20M item-item shape 59 GB of planes become 24, and a 47k-row shard of a 138k x 138k
-    // user-user build (52 GB of output) still fits one 180 GB GPU.
+    // footprint is bounded (default 12 GiB; SB2_SIM_PLANE_GIB / SB2_SIM_BAND_ROWS override) instead of growing with
+    // rows x n_x x 10: at the ml-20M item-item shape 59 GB of planes become 12 -- and the build gets faster, 1.04 ->
+    // 0.92 s (budget 48 / 24 / 12 / 6 / 3 GiB: 1.02 / 0.94 / 0.92 / 0.96 / 0.99 s) -- and a 47k-row shard of a
+    // 138k x 138k user-user build (52 GB of output) still fits one 180 GB GPU.
     const int rb0 = (int)(row_begin / TR), rb1 = (int)ceil_div(row_end, TR);
     int band_rb = rb1 - rb0;
     {
-        double gib = 24.0;
+        double gib = 12.0;
         if (const char* e = getenv("SB2_SIM_PLANE_GIB")) gib = std::max(0.001, atof(e));
         const double per_rb = (double)n_planes * (double)ld * 8.0 * TR;
         band_rb = (int)std::max(1.0, std::min((double)band_rb, floor(gib * 1073741824.0 / per_rb)));
