@@ -455,13 +455,16 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
         // every lane-group runs the same (CTA-uniform) number of rounds per wave, groups beyond the wave's
         // end carry a dummy rating with all stores predicated off: control flow stays warp-uniform, so the
         // shuffles can use the full-warp mask (a per-group mask costs MATCH / VOTE instructions per shuffle)
-        auto process = [&](int k, bool valid) {
-            int ul = 0, il = 0;
-            float r = 0.f;
+        // the record of a rating: fetched one wave ahead (shared-memory reads of read-only data), so that the wave's
+        // critical path starts at the row loads instead of at wave table -> record -> address
+        auto fetch = [&](int k, bool valid, int& ul, int& il, float& r) {
+            ul = 0; il = 0; r = 0.f;
             if (valid) {
                 if (k < staged) { ul = rul_c[k]; il = ril_c[k]; r = rr_c[k]; }
                 else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; }
             }
+        };
+        auto update = [&](int ul, int il, float r, bool valid) {
             float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
             float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
             float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
@@ -470,25 +473,43 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
             sgd_update<G, CH, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, valid, F4);
         };
-        for (int w = 0; w < NW - 1; ++w) {
-            const int wb = wave_c[w], we = wave_c[w + 1];
-            if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
-            // a warp whose first lane-group is already past the wave's end holds only dummies: skip it
-            // (warp-uniform test), it would otherwise compete for issue slots with the working warps
+        auto process = [&](int k, bool valid) {
+            int ul, il;
+            float r;
+            fetch(k, valid, ul, il, r);
+            update(ul, il, r, valid);
+        };
+        {
+            int wb = wave_c[0], we = wave_c[1];
+            int c_ul, c_il;
+            float c_r;
+            fetch(wb + gid, wb + gid < we, c_ul, c_il, c_r);
+            for (int w = 0; w < NW - 1; ++w) {
+                if (wb == we) break;  // colours are contiguous: an empty wave ends the cell (CTA-uniform)
+                // first round of the NEXT wave (wave NW - 1 is the tail: fetched and ignored)
+                const int nwb = we, nwe = wave_c[w + 2];
+                int n_ul, n_il;
+                float n_r;
+                fetch(nwb + gid, w + 2 < NW && nwb + gid < nwe, n_ul, n_il, n_r);
 #ifdef SB2_DSGD_WAVE_PROF
-            const long long w0 = clock64();
+                const long long w0 = clock64();
 #endif
-            for (int k = wb; k < we; k += W)
-                if (k + gid0 < we) process(k + gid, k + gid < we);
-            ++n_wave;
+                // a warp whose first lane-group is already past the wave's end holds only dummies: skip it
+                // (warp-uniform test), it would otherwise compete for issue slots with the working warps
+                if (wb + gid0 < we) update(c_ul, c_il, c_r, wb + gid < we);
+                for (int k = wb + W; k < we; k += W)
+                    if (k + gid0 < we) process(k + gid, k + gid < we);
+                ++n_wave;
 #ifdef SB2_DSGD_WAVE_PROF
-            const long long w1 = clock64();
-            __syncthreads();
-            t_act += w1 - w0;
-            t_bar += clock64() - w1;
+                const long long w1 = clock64();
+                __syncthreads();
+                t_act += w1 - w0;
+                t_bar += clock64() - w1;
 #else
-            __syncthreads();
+                __syncthreads();
 #endif
+                wb = nwb; we = nwe; c_ul = n_ul; c_il = n_il; c_r = n_r;
+            }
         }
         {
             const int wb = wave_c[NW - 1], we = wave_c[NW];
