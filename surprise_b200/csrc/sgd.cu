@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
     // and a single mbarrier cannot tell "one phase ahead" from "not yet" once two phases have completed.
     __shared__ __align__(8) uint64_t ring_bar[4];  // [0,1] data, [2,3] free
     if (tid == 0) {
-        for (int x = 0; x < 4; ++x) mbar_init_cta(&ring_bar[x], 1);
+        for (int x = 0; x < 4; ++x) mbar_init_cta(&ring_bar[x], (uint32_t)(nthr >> 5));  // one arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int nu_local = (a.n_users - ub + B - 1) / B;
@@ -528,18 +528,19 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             // reading its spare buffer (its previous push), copy my block into it through distributed shared
             // memory, tell it the data is there, tell my right neighbour that my block buffer is reusable,
             // and wait for my right neighbour's push into my own spare buffer.
-            if (n_push > 0 && tid == 0) mbar_wait_cluster(&ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
-            __syncthreads();
+            // Every thread waits for "free" itself and every warp signals for itself (mailboxes count one arrival
+            // per warp): no block barrier and no single-thread relay inside the hop.  __syncwarp orders the lanes'
+            // remote stores (and their reads of the block being sent) before lane 0's cluster-scope releases.
+            if (n_push > 0) mbar_wait_cluster(&ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
             const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
             const int n4 = a.ibuf >> 2;
             for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
-            __syncthreads();  // all of this CTA's remote stores precede thread 0's cluster-scope releases
-            if (tid == 0) {
+            __syncwarp();
+            if ((tid & 31) == 0) {
                 mbar_arrive_remote(left_data_bar + 8u * (n_push & 1));
                 mbar_arrive_remote(right_free_bar + 8u * (n_push & 1));
-                mbar_wait_cluster(&ring_bar[n_push & 1], (n_push >> 1) & 1);
             }
-            __syncthreads();
+            mbar_wait_cluster(&ring_bar[n_push & 1], (n_push >> 1) & 1);
             ++n_push;
             slot ^= 1;
             t_hop += clock64() - c3;
