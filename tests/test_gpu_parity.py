@@ -463,9 +463,10 @@ def test_u1_nmf_bit_exact(u1, u1_golden, u1_arrays):
         sb.NMF(init_low=-1)
 
 
-@pytest.mark.parametrize("f", (3, 15, 16, 40))
+@pytest.mark.parametrize("f", (3, 8, 15, 16, 24, 32, 40))
 def test_synthetic_nmf_bit_exact_host_abi(f):
-    """Through the host-buffer C-ABI, ragged segments, several group widths."""
+    """Through the host-buffer C-ABI, ragged segments, every group width of the fused pass (4 / 8 / 16 / 32 lanes) and
+    the three-kernel path (f > 32, and the biased model)."""
     d = synth.ratings(700, 300, 30_000, seed=f)
     u, i, r = d["train"]
     ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"])
