@@ -457,6 +457,37 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
         }
         for (int s = nc - 1; s >= 0; --s) add(P_T2, M, pa.c_panel[s], ldexp(1.0, 8 * s + 48 - 2 * FB));
     }
+    // Order the jobs so that the two accumulators of a launch share an operand panel on the same side where they can
+    // (3 operand tiles per pipeline stage instead of 4: less TMA and shared-memory fill traffic per MMA).  Jobs of
+    // one plane keep their relative order (the first one overwrites, the rest accumulate) and never share a launch.
+    {
+        std::vector<GemmJob> ordered;
+        std::vector<char> used(jobs.size(), 0);
+        auto first_of_plane = [&](size_t k) {  // no earlier unused job writes the same plane
+            for (size_t e = 0; e < k; ++e)
+                if (!used[e] && jobs[e].out == jobs[k].out) return false;
+            return true;
+        };
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            if (used[k]) continue;
+            used[k] = 1;
+            ordered.push_back(jobs[k]);
+            int best = -1, best_share = 0;
+            for (size_t m = k + 1; m < jobs.size(); ++m) {
+                if (used[m] || jobs[m].out == jobs[k].out || !first_of_plane(m)) continue;
+                const int share = (jobs[m].a == jobs[k].a) + (jobs[m].b == jobs[k].b);
+                if (share > best_share) { best_share = share; best = (int)m; }
+            }
+            if (best < 0)  // nothing shares: take the next eligible job so that launches stay full
+                for (size_t m = k + 1; m < jobs.size() && best < 0; ++m)
+                    if (!used[m] && jobs[m].out != jobs[k].out && first_of_plane(m)) best = (int)m;
+            if (best >= 0) {
+                used[best] = 1;
+                ordered.push_back(jobs[best]);
+            }
+        }
+        jobs.swap(ordered);
+    }
     const bool timing = getenv("SB2_SIM_TIMING") != nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (timing) {
