@@ -57,6 +57,18 @@ class Dataset(object):
 
     def _trainset_from_arrays(self, uids, iids, ratings):
         def first_appearance(a):
+            n = len(a)
+            if n and np.issubdtype(a.dtype, np.integer) and int(a.max()) - int(a.min()) <= max(4 * n, 10_000_000):
+                # integer raw ids in a modest range: O(N) table instead of a sort of all the ratings
+                lo = int(a.min())
+                shifted = (a - lo).astype(np.int64)
+                first = np.full(int(shifted.max()) + 1, n, dtype=np.int64)
+                first[shifted[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)   # repeated index: last write wins
+                present = np.nonzero(first < n)[0]
+                order = np.argsort(first[present], kind="stable")
+                rank = np.empty(len(first), dtype=np.int32)
+                rank[present[order]] = np.arange(len(present), dtype=np.int32)
+                return rank[shifted], (present[order] + lo).astype(a.dtype)
             uniq, first, inv = np.unique(a, return_index=True, return_inverse=True)
             order = np.argsort(first, kind="stable")          # uniq[order] is in first-appearance order
             rank = np.empty(len(uniq), dtype=np.int64)

@@ -39,6 +39,25 @@ def _dict_from_csr(ptr, idx, val):
     return out
 
 
+def _group_stable(key, other, val, n, counts):
+    """CSR of the ratings grouped by `key`, file order kept inside a group: (ptr int64, other, val).
+    A counting sort (scipy's coo_tocsr kernel, O(N)) when available; numpy's stable argsort otherwise
+    (2 s per side at 10M ratings)."""
+    ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+    if len(val) < 2 ** 31 - 1:
+        try:
+            from scipy.sparse import _sparsetools
+            bp = np.empty(n + 1, dtype=np.int32)
+            bj = np.empty(len(val), dtype=np.int32)
+            bx = np.empty(len(val), dtype=np.float64)
+            _sparsetools.coo_tocsr(n, int(other.max()) + 1 if len(other) else 1, len(val), key, other, val, bp, bj, bx)
+            return ptr, bj, bx
+        except Exception:  # pragma: no cover - scipy missing or its private kernel moved
+            pass
+    o = np.argsort(key, kind="stable")
+    return ptr, other[o], val[o]
+
+
 class Trainset(object):
     def __init__(self, ur, ir, n_users, n_items, n_ratings, rating_scale, offset, raw2inner_id_users,
                  raw2inner_id_items):
@@ -62,14 +81,12 @@ class Trainset(object):
         n_users = int(u.max()) + 1 if n_users is None else n_users
         n_items = int(i.max()) + 1 if n_items is None else n_items
         ts = cls(None, None, n_users, n_items, len(r), rating_scale, offset, None, None)
-        ou = np.argsort(u, kind="stable")
-        oi = np.argsort(i, kind="stable")
         cu = np.bincount(u, minlength=n_users)
         ci = np.bincount(i, minlength=n_items)
         if (cu == 0).any() or (ci == 0).any():
             raise ValueError("from_coo needs compact inner ids (every user / item id must have a rating)")
-        ts._ucsr = (np.concatenate(([0], np.cumsum(cu))).astype(np.int64), i[ou], r[ou])
-        ts._icsr = (np.concatenate(([0], np.cumsum(ci))).astype(np.int64), u[oi], r[oi])
+        ts._ucsr = _group_stable(u, i, r, n_users, cu)
+        ts._icsr = _group_stable(i, u, r, n_items, ci)
         ts._raw_uids, ts._raw_iids = raw_uids, raw_iids
         return ts
 

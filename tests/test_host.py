@@ -178,3 +178,35 @@ def test_synth_is_deterministic_and_compact():
     assert set(np.unique(r)) <= {1., 2., 3., 4., 5.}
     # first-appearance order
     assert np.array_equal(np.unique(u, return_index=True)[1].argsort(), np.arange(a["n_users"]))
+
+
+def test_trainset_ingest_fast_paths_match_reference_order():
+    """Array ingest: the O(N) counting-sort grouping of Trainset.from_coo and the O(N) table for
+    integer raw ids must give what the reference's dict construction gives: inner ids in first-appearance order
+    (dataset.py:219-234), ur[u] / ir[i] in file order (trainset.py)."""
+    import surprise_b200 as sb
+    from surprise_b200 import trainset
+    rng = np.random.RandomState(3)
+    n = 50_000
+    raw_u = rng.randint(-40, 3000, n) * 7          # gaps and negative ids
+    raw_i = rng.randint(10, 900, n)
+    r = rng.randint(1, 6, n).astype(np.float64)
+    ts = sb.Dataset.load_from_arrays(raw_u, raw_i, r, sb.Reader(rating_scale=(1, 5))).build_full_trainset()
+    # reference semantics restated with dicts
+    u2i, i2i, ur, ir = {}, {}, {}, {}
+    for a, b, c in zip(raw_u.tolist(), raw_i.tolist(), r.tolist()):
+        uu = u2i.setdefault(a, len(u2i)); ii = i2i.setdefault(b, len(i2i))
+        ur.setdefault(uu, []).append((ii, c)); ir.setdefault(ii, []).append((uu, c))
+    assert ts.n_users == len(u2i) and ts.n_items == len(i2i)
+    for k in (0, 1, 5, len(u2i) - 1):
+        assert ts.ur[k] == ur[k]
+    for k in (0, 3, len(i2i) - 1):
+        assert ts.ir[k] == ir[k]
+    assert ts.to_inner_uid(raw_u[0]) == 0 and ts.to_raw_uid(0) == raw_u[0]
+    # the grouping kernel against numpy's stable argsort
+    u, i, rr = ts.coo()
+    perm = rng.permutation(len(rr))
+    u, i, rr = u[perm], i[perm], rr[perm]
+    o = np.argsort(i, kind="stable")
+    ptr, other, val = trainset._group_stable(i, u, rr, ts.n_items, np.bincount(i, minlength=ts.n_items))
+    assert np.array_equal(other, u[o]) and np.array_equal(val, rr[o]) and ptr[-1] == len(rr)
