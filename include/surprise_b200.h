@@ -214,6 +214,7 @@ void sb2_nmf_plan_destroy(sb2_nmf_plan* plan);
  * NMF.estimate (:737-761) and SVDpp.estimate (:506-522; yj != NULL) called once per pair by
  * AlgoBase.test (algo_base.py:191-218).  u[k] < 0 / i[k] < 0 encode an unknown user / item.
  * impossible[k] = 1 where the reference raises PredictionImpossible.
+ * n_factors = 0 with biased = 1 is BaselineOnly.estimate (baseline_only.py:33-46): (mu + bu[u]) + bi[i], pu / qi unused.
  * ------------------------------------------------------------------------------------------------ */
 int sb2_mf_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, int n_factors, int biased,
                        double global_mean, const double* pu, const double* qi, const double* bu,

@@ -259,6 +259,22 @@ def test_u1_baselines_bit_exact(u1, u1_golden):
         sb.BaselineOnly(bsl_options={"method": "nope"}).fit(ts)
 
 
+def test_u1_baseline_only_predictions(u1, u1_golden):
+    """BaselineOnly.test is batched through the estimate kernel with zero factors: (mu + b_u) + b_i with unknown ids
+    skipped, the reference's additions in the reference's order -- RMSE / MAE equal the golden to the last digit."""
+    ts, testset = u1
+    for method, tag in (("als", "BaselineOnly_als"), ("sgd", "BaselineOnly_sgd")):
+        algo = sb.BaselineOnly(bsl_options={"method": method}).fit(ts)
+        preds = algo.test(testset)
+        g = u1_golden["algos"][tag]
+        assert repr(float(sb.accuracy.rmse(preds, verbose=False))) == g["rmse"]
+        assert repr(float(sb.accuracy.mae(preds, verbose=False))) == g["mae"]
+        assert sum(p.details["was_impossible"] for p in preds) == g["n_impossible"] == 0
+        uid, iid, _ = testset[3]
+        assert algo.predict(uid, iid).est == preds[3].est
+        assert pickle.loads(pickle.dumps(algo)).predict(uid, iid).est == preds[3].est
+
+
 # ---- k-NN -----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("orient", ("item", "user"))
 @pytest.mark.parametrize("kind", KINDS)
