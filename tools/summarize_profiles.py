@@ -99,5 +99,44 @@ for key, rep in (('dsgd_svd_kernel_dram_bytes_per_launch', 'svd_prof.ncu-rep'), 
 json.dump(traffic, open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
 notes = open(os.path.join(P, 'r1_notes.md')).read() if os.path.exists(os.path.join(P, 'r1_notes.md')) else ''
 out.append(notes)
+def headline():
+    """One table of every measured kernel / config, read from the JSON artefacts next to this file."""
+    def load(name):
+        f = os.path.join(P, name)
+        return json.load(open(f)) if os.path.exists(f) else {}
+    b, cfg, pred = load('r1_bench_n1.json'), load('r1_configs_full_shape.json'), load('r1_predict.json')
+    s1, s2, s8 = load('r1_scale_n1.json'), load('r1_scale_n2.json'), load('r1_scale_n8.json')
+    rows = ['## Headline numbers (one B200 unless stated)\n',
+            '| What | Measured | Bound / fraction | Source |', '|---|---|---|---|']
+    if b:
+        r = b['roofline']
+        rows.append('| SVD f=100, 20 epochs, ml-1M shape (bench.py) | %.3g rating-updates/s resident, %.3g end to end; kernel %.2f ms | '
+                    'on-chip latency; %.2f of measured HBM peak on algorithmic bytes, DRAM traffic %.1f MB per fit | r1_bench_n1.json |'
+                    % (b['value'], b['e2e']['value'], r['kernel_ms_per_launch'], r['frac'], (r['traffic'] or 0) / 1e6))
+        rows.append('| reference Cython SVD.sgd on the same box | %.3g rating-updates/s (1 core) | - | r1_bench_n1.json cpu_baseline |' % b['cpu_baseline']['value'])
+    c3, c4, c5 = cfg.get('c3', {}), cfg.get('c4', {}), cfg.get('c5', {})
+    if c3:
+        rows.append('| pearson_baseline item-item build, ml-20M shape | %.3f s (cosine %.3f s); max abs err %.2g on 20k sampled pairs | tensor (int8): see note in the file | r1_configs_full_shape.json |'
+                    % (c3['sim_build_s'], c3['cosine_build_s'], c3['max_abs_err_vs_oracle_20000_sampled_pairs']))
+    for name, sc in (('2', s2), ('8', s8)):
+        if sc.get('c3_pearson_baseline_build_s'):
+            rows.append('| same, %s GPUs (symmetric shards + NCCL exchange) | %.3f s (cosine %.3f s) | - | r1_scale_n%s.json |'
+                        % (name, sc['c3_pearson_baseline_build_s'], sc['c3_cosine_build_s'], name))
+    if c4:
+        rows.append('| SVD++ f=20, 20 epochs, ml-10M shape | %.3f s, held-out RMSE %.5f (sequential oracle %.5f) | - | r1_configs_full_shape.json |'
+                    % (c4['fit_s'], c4['heldout_rmse'], c4['oracle_heldout_rmse']))
+    if c5:
+        rows.append('| NMF f=15, 50 epochs, Netflix shape | %.3f s = %.3g visits/s, bit-exact vs oracle: %s | L1TEX data pipe; %.2f of measured HBM peak on algorithmic bytes | r1_configs_full_shape.json |'
+                    % (c5['fit_s'], c5['rating_visits_per_s'], c5['two_epochs_bit_exact_vs_oracle'], c5['frac_of_measured_hbm']))
+    if s2.get('c5_nmf_epochs_s'):
+        rows.append('| same, 2 GPUs (sharded accumulators, all-gather per epoch) | %.3f s of epochs | - | r1_scale_n2.json |' % s2['c5_nmf_epochs_s'])
+    if pred:
+        rows.append('| k-NN estimate (k=40), ml-1M shape | %.3g pairs/s | issue (ordered selection); %.2f of HBM peak | r1_predict.json |'
+                    % (pred['knn_basic']['pairs_per_s'], pred['knn_basic']['frac_of_measured_hbm']))
+        rows.append('| factor-model estimate f=100 | %.3g pairs/s | L2 gather; %.2f of HBM peak | r1_predict.json |'
+                    % (pred['mf_predict_f100']['pairs_per_s'], pred['mf_predict_f100']['frac_of_measured_hbm']))
+    rows.append('')
+    return rows
+out = headline() + out
 open(os.path.join(P, 'r1_summary.md'), 'w').write('# Round 1 profile summaries (B200, sm_100a)\n\nRaw artefacts next to this file: r1_*_launches.csv (ncu launch lists), r1_bench_n1.json / r1_bench_n2.json (bench lines of\nthe same build), r1_configs_full_shape.json (BASELINE.json configs 3-5 at full shape on one GPU), r1_dsgd_*.log\n(in-kernel phase counters, sb2_svd_plan_profile).\n\n' + '\n'.join(out))
 print('\n'.join(out)[:3000])
