@@ -153,11 +153,38 @@ void sb2_svd_plan_destroy(sb2_svd_plan* plan);
 /* algorithmic bytes per rating update of the plan's kernel (2*(2f+2)*4 + 12 for SVD) */
 int64_t sb2_svd_plan_bytes_per_update(const sb2_svd_plan* plan);
 int sb2_svd_plan_grid(const sb2_svd_plan* plan, int* n_blocks, int* n_sub);
-/* Multi-GPU ring (DSGD across ranks): run the plan on caller-owned fp32 DEVICE factor buffers laid out
- * rows x sb2_svd_plan_stride() (n_factors rounded up to 4, zero padded); the item-side buffers are the
- * block that rotates rank -> rank between sub-epochs. */
-int sb2_svd_plan_bind_dev(sb2_svd_plan* plan, float* pu, float* qi, float* bu, float* bi);
-int sb2_svd_plan_stride(const sb2_svd_plan* plan);
+/* Synchronises `stream` and reports whether the persistent kernel ran to completion: every wait of a CTA for a
+ * neighbour CTA / rank is bounded (~6 s); if a partner was never scheduled (SMs held by another persistent kernel,
+ * a dead peer rank) the launch drains and this returns SB2_ERR_CUDA instead of the GPU hanging.  The host forms
+ * (sb2_svd_fit, sb2_svdpp_fit) check it themselves. */
+int sb2_svd_plan_status(sb2_svd_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU ring (DSGD strata across ranks, one process per GPU; SURVEY.md 8e "SVD (DSGD)").  Replaces the same
+ * loop, matrix_factorization.pyx:241-262 (SVD) / :466-498 (SVD++), for a trainset sharded by user.
+ * Rank g of `world` owns the users u % world == g for the whole fit and, in sub-epoch E, the item super-block
+ * (g + E) % world; the kernel itself hands every finished item block to rank g - 1 over NVLink (stores through the
+ * peer mapping + system-scope release / acquire flags) -- ONE persistent launch per rank for a whole SVD fit.
+ *   create:  every rank passes the SAME global COO (DEVICE arrays) and its (rank, world); it keeps its own ratings.
+ *   connect: exchange the 64-byte handles between the processes (e.g. torch.distributed.all_gather) and pass the
+ *            left (rank - 1) and right (rank + 1) neighbours' handles; or, inside one process, the plans themselves.
+ *   reset:   sb2_svd_plan_reset_dev with the WHOLE initial matrices; then synchronise the ranks (any collective)
+ *            before run: reset clears the mailboxes the neighbours write into.
+ *   run:     sb2_svd_plan_run (SVD), or per epoch sb2_svd_ring_epoch_dev(phase 0) -> all-reduce(SUM) of `exchange`
+ *            (n_items x (row_stride + 1) fp32, DEVICE) over the ranks -> sb2_svd_ring_epoch_dev(phase 1) (SVD++: the
+ *            per-item sums of the y_j application span the users of all ranks).
+ *   read:    sb2_svd_plan_read_dev returns the rank's OWN rows (n_users_local x f, n_items_local x f, local order:
+ *            global id = rank + local * world); synchronise the ranks before reading / destroying.
+ * ------------------------------------------------------------------------------------------------ */
+int sb2_svd_ring_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
+                            const int32_t* ui_idx, int rank, int world, void* stream, sb2_svd_plan** out);
+int sb2_svd_ring_ipc_handle(const sb2_svd_plan* plan, unsigned char* handle64);
+int sb2_svd_ring_connect_ipc(sb2_svd_plan* plan, const unsigned char* left64, const unsigned char* right64);
+int sb2_svd_ring_connect_local(sb2_svd_plan* plan, sb2_svd_plan* left, sb2_svd_plan* right);
+int sb2_svd_ring_epoch_dev(sb2_svd_plan* plan, int phase, float* exchange, void* stream);
+int sb2_svd_ring_info(const sb2_svd_plan* plan, int64_t* n_users_local, int64_t* n_items_local,
+                      int64_t* n_ratings_local, int* row_stride);
 /* Per-CTA counters of the last run, cycles_host[n_blocks][8] (n_blocks from sb2_svd_plan_grid): SM cycles in
  * {ring wait, item-block load, rating updates, write-back, lane-group-0 updates}, then the number of
  * lane-group-0 updates, the number of waves, 0. */

@@ -62,8 +62,13 @@ SIGNATURES = {
     "sb2_svd_plan_destroy": (None, [_vp]),
     "sb2_svd_plan_bytes_per_update": (_i64, [_vp]),
     "sb2_svd_plan_grid": (_int, [_vp, _vp, _vp]),
-    "sb2_svd_plan_bind_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
-    "sb2_svd_plan_stride": (_int, [_vp]),
+    "sb2_svd_plan_status": (_int, [_vp, _vp]),
+    "sb2_svd_ring_create_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp, _vp, _int, _int, _vp, _vp]),
+    "sb2_svd_ring_ipc_handle": (_int, [_vp, _vp]),
+    "sb2_svd_ring_connect_ipc": (_int, [_vp, _vp, _vp]),
+    "sb2_svd_ring_connect_local": (_int, [_vp, _vp, _vp]),
+    "sb2_svd_ring_epoch_dev": (_int, [_vp, _int, _vp, _vp]),
+    "sb2_svd_ring_info": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "sb2_svd_plan_profile": (_int, [_vp, _vp]),
     "sb2_svdpp_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb2_svdpp_fit": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -75,15 +75,19 @@ int slope_one_predict_dev(int64_t n_pairs, const int32_t* u, const int32_t* i, i
                           double* est, uint8_t* impossible, cudaStream_t st);
 int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
                         const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
-                        const int32_t* ui_idx, cudaStream_t st, sb2_svd_plan** out);
+                        const int32_t* ui_idx, int rank, int world, cudaStream_t st, sb2_svd_plan** out);
 int svd_plan_reset_dev(sb2_svd_plan* p, const double* pu0, const double* qi0, const double* yj0, cudaStream_t st);
 int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st);
 int svd_plan_read_dev(sb2_svd_plan* p, double* pu, double* qi, double* bu, double* bi, double* yj, cudaStream_t st);
 void svd_plan_destroy(sb2_svd_plan* p);
 int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p);
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w);
-void svd_plan_bind(sb2_svd_plan* p, float* pu, float* qi, float* bu, float* bi);
-int svd_plan_stride(const sb2_svd_plan* p);
+int svd_plan_status(sb2_svd_plan* p, cudaStream_t st);
+int svd_ring_epoch_dev(sb2_svd_plan* p, int phase, float* xch, cudaStream_t st);
+int svd_ring_ipc_handle(const sb2_svd_plan* p, unsigned char* out64);
+int svd_ring_connect_ipc(sb2_svd_plan* p, const unsigned char* left64, const unsigned char* right64);
+int svd_ring_connect_local(sb2_svd_plan* p, sb2_svd_plan* left, sb2_svd_plan* right);
+void svd_ring_info(const sb2_svd_plan* p, int64_t* nu_loc, int64_t* ni_loc, int64_t* n_loc, int* stride);
 int svd_plan_profile(const sb2_svd_plan* p, long long* out_host);
 void svd_plan_dims(const sb2_svd_plan* p, int64_t* n_users, int64_t* n_items, int* f, int* with_yj);
 
@@ -255,12 +259,13 @@ static int svd_like_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const i
                             const double* r, const int64_t* u_ptr, const int32_t* ui_idx, const sb2_sgd_params* prm,
                             double* pu, double* qi, double* yj, double* bu, double* bi, cudaStream_t st) {
     sb2_svd_plan* plan = nullptr;
-    SB2_TRY(svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, yj != nullptr, u_ptr, ui_idx, st, &plan));
+    SB2_TRY(svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, yj != nullptr, u_ptr, ui_idx, 0, 1, st, &plan));
     int rc = svd_plan_reset_dev(plan, pu, qi, yj, st);
     if (rc == SB2_OK) rc = svd_plan_run(plan, prm->n_epochs, st);
     if (rc == SB2_OK) rc = svd_plan_read_dev(plan, pu, qi, bu, bi, yj, st);
-    if (rc == SB2_OK && cudaStreamSynchronize(st) != cudaSuccess) {
-        set_error("svd_fit: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == SB2_OK) rc = svd_plan_status(plan, st);  // synchronises; a wait that hit its deadline is an error
+    if (rc == SB2_OK && cudaGetLastError() != cudaSuccess) {
+        set_error("svd_fit: CUDA error after the fit");
         rc = SB2_ERR_CUDA;
     }
     svd_plan_destroy(plan);
@@ -351,7 +356,7 @@ int sb2_svd_plan_create(int64_t n_users, int64_t n_items, int64_t n, const int32
     }
     int rc = svd_plan_create_dev(n_users, n_items, n, d_u.as<int32_t>(), d_i.as<int32_t>(), d_r.as<double>(), prm,
                                  with_yj, with_yj ? d_up.as<int64_t>() : nullptr, with_yj ? d_i.as<int32_t>() : nullptr,
-                                 st, out);
+                                 0, 1, st, out);
     cudaStreamSynchronize(st);
     return rc;
 }
@@ -380,8 +385,38 @@ int sb2_svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const i
                             const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
                             const int32_t* ui_idx, void* stream, sb2_svd_plan** out) {
     SB2_TRY(ensure_device());
-    return svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, with_yj, u_ptr, ui_idx, (cudaStream_t)stream, out);
+    return svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, with_yj, u_ptr, ui_idx, 0, 1, (cudaStream_t)stream,
+                               out);
 }
+int sb2_svd_ring_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
+                            const int32_t* ui_idx, int rank, int world, void* stream, sb2_svd_plan** out) {
+    SB2_TRY(ensure_device());
+    return svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, with_yj, u_ptr, ui_idx, rank, world,
+                               (cudaStream_t)stream, out);
+}
+int sb2_svd_ring_ipc_handle(const sb2_svd_plan* plan, unsigned char* handle64) {
+    return svd_ring_ipc_handle(plan, handle64);
+}
+int sb2_svd_ring_connect_ipc(sb2_svd_plan* plan, const unsigned char* left64, const unsigned char* right64) {
+    return svd_ring_connect_ipc(plan, left64, right64);
+}
+int sb2_svd_ring_connect_local(sb2_svd_plan* plan, sb2_svd_plan* left, sb2_svd_plan* right) {
+    if (!plan || !left || !right) {
+        set_error("svd_ring_connect_local: null plan");
+        return SB2_ERR_INVALID;
+    }
+    return svd_ring_connect_local(plan, left, right);
+}
+int sb2_svd_ring_epoch_dev(sb2_svd_plan* plan, int phase, float* exchange, void* stream) {
+    return svd_ring_epoch_dev(plan, phase, exchange, (cudaStream_t)stream);
+}
+int sb2_svd_ring_info(const sb2_svd_plan* plan, int64_t* n_users_local, int64_t* n_items_local, int64_t* n_ratings_local,
+                      int* row_stride) {
+    svd_ring_info(plan, n_users_local, n_items_local, n_ratings_local, row_stride);
+    return SB2_OK;
+}
+int sb2_svd_plan_status(sb2_svd_plan* plan, void* stream) { return svd_plan_status(plan, (cudaStream_t)stream); }
 int sb2_svd_plan_reset_dev(sb2_svd_plan* plan, const double* pu, const double* qi, const double* yj, void* stream) {
     return svd_plan_reset_dev(plan, pu, qi, yj, (cudaStream_t)stream);
 }
@@ -418,15 +453,6 @@ int sb2_svd_plan_read(sb2_svd_plan* plan, double* pu, double* qi, double* bu, do
 
 void sb2_svd_plan_destroy(sb2_svd_plan* plan) { svd_plan_destroy(plan); }
 int64_t sb2_svd_plan_bytes_per_update(const sb2_svd_plan* plan) { return svd_plan_bytes_per_update(plan); }
-int sb2_svd_plan_bind_dev(sb2_svd_plan* plan, float* pu, float* qi, float* bu, float* bi) {
-    if (!plan || !pu || !qi || !bu || !bi) {
-        set_error("svd_plan_bind: null argument");
-        return SB2_ERR_INVALID;
-    }
-    svd_plan_bind(plan, pu, qi, bu, bi);
-    return SB2_OK;
-}
-int sb2_svd_plan_stride(const sb2_svd_plan* plan) { return svd_plan_stride(plan); }
 int sb2_svd_plan_profile(const sb2_svd_plan* plan, int64_t* cycles_host) {
     return svd_plan_profile(plan, reinterpret_cast<long long*>(cycles_host));
 }

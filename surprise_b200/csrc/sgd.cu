@@ -57,6 +57,23 @@ struct DsgdArgs {
     float mu, lr_bu, lr_bi, lr_pu, lr_qi, reg_bu, reg_bi, reg_pu, reg_qi, lr_yj, reg_yj;
     int n_epochs;
     long long* prof;                    // optional: [CTA][8]: cycles in {ring wait, block load, updates, write-back, group-0 updates}, #group-0 updates, #waves, 0
+    int* status;                        // != 0: a wait ran into its deadline (a CTA / a peer rank was never scheduled)
+    // ---- ring over P ranks (one process per GPU; P == 1: everything below is unused) --------------------------
+    // Rank g owns the users u % P == g for the whole fit and, during sub-epoch E (counted from the start of the
+    // fit), the item super-block (g + E) % P, whose (qi, bi) rows live in ring_qi / ring_bi[E & 1].  The CTA that
+    // finishes an item block in the last stratum of a sub-epoch stores it straight into the LEFT neighbour's
+    // buffer (E + 1) & 1 over NVLink (peer-mapped pointers) and publishes it with a system-scope release on the
+    // neighbour's rflags; the neighbour returns a credit once it has consumed the slot it is about to lose.
+    int P, rank, E_base;                // E_base: sub-epochs done by earlier launches (SVD++ launches once per epoch)
+    int n_items_glob;                   // items of super-block sb: (n_items_glob - sb + P - 1) / P
+    float* ring_qi[2];
+    float* ring_bi[2];
+    float* left_qi[2];                  // the left neighbour's ring buffers (rank - 1)
+    float* left_bi[2];
+    int* rflags;                        // [B] written by the RIGHT neighbour: sub-epochs whose block it has delivered
+    int* left_rflags;
+    int* credit;                        // [B] written by the LEFT neighbour: sub-epochs of that block it has consumed
+    int* right_credit;
 };
 
 __device__ __forceinline__ int ld_relaxed(const int* p) {
@@ -67,6 +84,52 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
 __device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Every wait of the persistent kernel is bounded: if a partner CTA (or a peer rank) is never scheduled -- SMs held
+// by another persistent kernel, an MPS peer, a rank that died -- the waiter gives up after SPIN_LIMIT cycles, raises
+// *status and stops waiting for anything else, so the launch drains and the host reports SB2_ERR_CUDA instead of a
+// hung GPU.  The clock and *status are looked at once every 256 polls only.
+constexpr long long SPIN_LIMIT = 12ll << 30;  // ~6.5 s at 1.97 GHz
+struct SpinGuard {
+    int* status;
+    bool dead;
+    __device__ __forceinline__ bool expired(unsigned& polls, long long& t0) {
+        if ((++polls & 255u) != 0) return false;
+        if (t0 == 0) { t0 = clock64(); return false; }
+        if (*reinterpret_cast<volatile int*>(status) != 0 || clock64() - t0 > SPIN_LIMIT) {
+            atomicExch(status, 1);
+            dead = true;
+            return true;
+        }
+        return false;
+    }
+};
+enum { WAIT_EQ_GPU = 0, WAIT_GE_SYS = 1 };
+template <int MODE>
+__device__ __forceinline__ void wait_counter(SpinGuard& g, const int* p, int want) {
+    if (g.dead) return;
+    unsigned polls = 0;
+    long long t0 = 0;
+    if (MODE == WAIT_EQ_GPU) {
+        while (ld_relaxed(p) != want)
+            if (g.expired(polls, t0)) return;
+        fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
+    } else {
+        while (ld_relaxed_sys(p) < want)
+            if (g.expired(polls, t0)) return;
+        fence_acquire_sys();
+    }
 }
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -87,18 +150,25 @@ __device__ __forceinline__ void mbar_init_cta(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "MBW_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra MBW_DONE;\n\t"
-        "bra MBW_LOOP;\n\t"
-        "MBW_DONE:\n\t"
-        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(SpinGuard& g, uint64_t* bar, uint32_t parity) {
+    if (g.dead) return;
+    unsigned polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait_cluster(bar, parity))
+        if (g.expired(polls, t0)) return;
 }
 __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -318,8 +388,8 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
     float* isq_s = bu_s + (SU ? a.max_ul : 0);
     float* cnt_s = isq_s + ((SU && PP) ? a.max_ul : 0);
     int* wave_s = reinterpret_cast<int*>(cnt_s + ((SU && PP) ? a.max_ul : 0));
-    int* coff_s = wave_s + 2 * (NW + 1);      // [2 * B]: cell begin / end per stratum (wave_s: two buffers)
-    int* rul_s = coff_s + 2 * B;              // records: two buffers of rec_cap each
+    int* coff_s = wave_s + 2 * (NW + 1);      // [2 * P * B]: cell begin / end per stratum (wave_s: two buffers)
+    int* rul_s = coff_s + 2 * a.P * B;        // records: two buffers of rec_cap each
     int* ril_s = rul_s + 2 * a.rec_cap;
     float* rr_s = reinterpret_cast<float*>(ril_s + 2 * a.rec_cap);
 
@@ -348,11 +418,12 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             }
         }
     }
-    for (int s = tid; s < B; s += nthr) {
+    for (int s = tid; s < a.P * B; s += nthr) {
         coff_s[2 * s] = a.cell_off[(size_t)s * B + ub];
         coff_s[2 * s + 1] = a.cell_off[(size_t)s * B + ub + 1];
     }
     __syncthreads();
+    SpinGuard guard{a.status, false};
 
     long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, n_wave = 0, t_hop = 0;
 #ifdef SB2_DSGD_WAVE_PROF
@@ -383,7 +454,7 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
     // records + wave table of step j go to buffer (j & 1) with cp.async, issued one step ahead: they land while
     // the previous stratum is being updated instead of costing an L2 round trip at the head of every stratum
     auto prefetch = [&](int j) {
-        const int s = a.s_begin + j % n_strata;
+        const int s = a.s_begin + j % n_strata;   // stratum within the epoch, [0, P * B)
         const int k0 = coff_s[2 * s];
         const int staged = min(coff_s[2 * s + 1] - k0, a.rec_cap);
         int* rul = rul_s + (size_t)(j & 1) * a.rec_cap;
@@ -399,15 +470,30 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
         for (int x = tid; x <= NW; x += nthr) cp_async4(wave + x, wsrc + x);
     };
     if (n_steps > 0) prefetch(0);
+    const int P = a.P;
     for (int step = 0; step < n_steps; ++step) {
         const int ep = step / n_strata;
-        const int s = a.s_begin + (step - ep * n_strata);
+        const int sg = a.s_begin + (step - ep * n_strata);   // stratum within the epoch, [0, P * B)
+        // ranks: sub-epoch S of the epoch, E sub-epochs since the fit began; launches of a ring cover whole epochs
+        const int S = P > 1 ? sg / B : 0;
+        const int s = sg - S * B;
+        const int E = a.E_base + ep * P + S;
         const int T = s / C, t = s - T * C;
         const int D = (Cl + T) % K;
-        const int gstep = ep * n_outer + (T - T_begin);
-        const bool first = (s == a.s_begin) || t == 0;       // of this outer step within the launch
-        const bool last = (s + 1 == a.s_end) || t + 1 == C;
-        const bool wait_flag = first && step != 0;
+        const int gstep = P > 1 ? E * K + T : ep * n_outer + (T - T_begin);
+        const bool first = (sg == a.s_begin) || t == 0;       // of this outer step within the launch
+        const bool last = (sg + 1 == a.s_end) || t + 1 == C;
+        const bool wait_flag = P > 1 ? (first && gstep != 0) : (first && step != 0);
+        // where this sub-epoch's item rows live in global memory (the L2 hand-off between clusters, block loads)
+        float* g_qi = a.qi;
+        float* g_bi = a.bi;
+        int n_items_sb = a.n_items;
+        if (P > 1) {
+            g_qi = a.ring_qi[E & 1];
+            g_bi = a.ring_bi[E & 1];
+            int sb = (a.rank + E) % P;
+            n_items_sb = (a.n_items_glob - sb + P - 1) / P;
+        }
         const int* rul_c = rul_s + (size_t)(step & 1) * a.rec_cap;
         const int* ril_c = ril_s + (size_t)(step & 1) * a.rec_cap;
         const float* rr_c = rr_s + (size_t)(step & 1) * a.rec_cap;
@@ -418,17 +504,19 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
         float* qi_s = ibuf_s + (size_t)slot * a.ibuf;
         float* bi_s = qi_s + (size_t)a.max_il * FP;
         const long long c0 = clock64();
-        const int k0 = coff_s[2 * s], cnt = coff_s[2 * s + 1] - k0;
+        const int k0 = coff_s[2 * sg], cnt = coff_s[2 * sg + 1] - k0;
         const int staged = min(cnt, a.rec_cap);
         cp_async_wait_all();  // this stratum's records (issued during the previous stratum)
         if (wait_flag && tid == 0) {
-            while (ld_relaxed(a.flags + ib) != gstep) { /* previous cluster still owns the super-block */ }
-            fence_acquire();  // relaxed polls + one acquire fence: no L1 invalidation per poll
+            // T > 0 (or one rank): the previous cluster still owns the block; T == 0 of a ring: the right
+            // neighbour rank delivers it at the end of ITS previous sub-epoch (system-scope release over NVLink)
+            if (P > 1 && T == 0) wait_counter<WAIT_GE_SYS>(guard, a.rflags + ib, E);
+            else wait_counter<WAIT_EQ_GPU>(guard, a.flags + ib, gstep);
         }
         __syncthreads();
         if (step + 1 < n_steps) prefetch(step + 1);
         const long long c1 = clock64();
-        const int ni_local = (a.n_items - ib + B - 1) / B;
+        const int ni_local = (n_items_sb - ib + B - 1) / B;
         if (SI && first) {
             const int total = ni_local * F4;
             for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
@@ -438,7 +526,7 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
                     const int x = t0 + q * nthr;
                     if (x < total) {
                         const int l = x / F4, cc = x - l * F4;
-                        v[q] = __ldcg(reinterpret_cast<const float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc);
+                        v[q] = __ldcg(reinterpret_cast<const float4*>(g_qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc);
                     }
                 }
 #pragma unroll
@@ -447,8 +535,11 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
                     if (x < total) reinterpret_cast<float4*>(qi_s)[x] = v[q];
                 }
             }
-            for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(a.bi + ib + (size_t)l * B);
+            for (int l = tid; l < ni_local; l += nthr) bi_s[l] = __ldcg(g_bi + ib + (size_t)l * B);
             __syncthreads();
+            // ring: this was the last read of slot ib of buffer E & 1 in this sub-epoch (the block leaves the rank
+            // at the end of the outer step): the right neighbour may overwrite it with the block of sub-epoch E + 2
+            if (P > 1 && T == K - 1 && tid == 0) st_release_sys(a.right_credit + ib, E + 1);
         }
         const long long c2 = clock64();
 
@@ -466,9 +557,9 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
         };
         auto update = [&](int ul, int il, float r, bool valid) {
             float* prow = SU ? pu_s + (size_t)ul * US : a.pu + ((size_t)(ub + (size_t)ul * B)) * US;
-            float* qrow = SI ? qi_s + (size_t)il * FP : a.qi + ((size_t)(ib + (size_t)il * B)) * FP;
+            float* qrow = SI ? qi_s + (size_t)il * FP : g_qi + ((size_t)(ib + (size_t)il * B)) * FP;
             float* bup = SU ? bu_s + ul : a.bu + ub + (size_t)ul * B;
-            float* bip = SI ? bi_s + il : a.bi + ib + (size_t)il * B;
+            float* bip = SI ? bi_s + il : g_bi + ib + (size_t)il * B;
             const float* isqp = PP ? (SU ? isq_s + ul : a.isq + ub + (size_t)ul * B) : nullptr;
             float* cntp = PP ? (SU ? cnt_s + ul : a.cnt + ub + (size_t)ul * B) : nullptr;
             sgd_update<G, CH, SU, SI, BIASED, PP>(a, prow, qrow, bup, bip, isqp, cntp, r, gl, valid, F4);
@@ -531,7 +622,7 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             // Every thread waits for "free" itself and every warp signals for itself (mailboxes count one arrival
             // per warp): no block barrier and no single-thread relay inside the hop.  __syncwarp orders the lanes'
             // remote stores (and their reads of the block being sent) before lane 0's cluster-scope releases.
-            if (n_push > 0) mbar_wait_cluster(&ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
+            if (n_push > 0) mbar_wait_cluster(guard, &ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
             const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
             const int n4 = a.ibuf >> 2;
             for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
@@ -540,25 +631,40 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
                 mbar_arrive_remote(left_data_bar + 8u * (n_push & 1));
                 mbar_arrive_remote(right_free_bar + 8u * (n_push & 1));
             }
-            mbar_wait_cluster(&ring_bar[n_push & 1], (n_push >> 1) & 1);
+            mbar_wait_cluster(guard, &ring_bar[n_push & 1], (n_push >> 1) & 1);
             ++n_push;
             slot ^= 1;
             t_hop += clock64() - c3;
         } else {
-            // slow hop: hand the block to the next cluster through L2
+            // slow hop: hand the block to the next cluster through L2 -- or, at the end of a ring's sub-epoch, to
+            // the left neighbour RANK: the rows are stored straight into its buffer (E + 1) & 1 through the
+            // peer mapping (NVLink), once it has returned the credit for that slot
+            float* d_qi = g_qi;
+            float* d_bi = g_bi;
+            const bool to_peer = P > 1 && T == K - 1;
+            if (to_peer) {
+                d_qi = a.left_qi[(E + 1) & 1];
+                d_bi = a.left_bi[(E + 1) & 1];
+                if (tid == 0) wait_counter<WAIT_GE_SYS>(guard, a.credit + ib, E);
+                __syncthreads();
+            }
             if (SI) {
                 for (int l = tid / F4, cc = tid % F4; l < ni_local; ) {
-                    __stcg(reinterpret_cast<float4*>(a.qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc,
+                    __stcg(reinterpret_cast<float4*>(d_qi + ((size_t)(ib + (size_t)l * B)) * FP) + cc,
                            reinterpret_cast<const float4*>(qi_s)[l * F4 + cc]);
                     cc += nthr % F4; l += nthr / F4;
                     if (cc >= F4) { cc -= F4; ++l; }
                 }
                 if (BIASED)
-                    for (int l = tid; l < ni_local; l += nthr) __stcg(a.bi + ib + (size_t)l * B, bi_s[l]);
+                    for (int l = tid; l < ni_local; l += nthr) __stcg(d_bi + ib + (size_t)l * B, bi_s[l]);
             }
-            // bar.sync orders every thread's stores before thread 0's gpu-scope release (cumulativity)
+            // bar.sync orders every thread's stores before thread 0's release (cumulativity); system scope when
+            // the consumer is another GPU
             __syncthreads();
-            if (tid == 0) st_release(a.flags + ib, gstep + 1);
+            if (tid == 0) {
+                if (to_peer) st_release_sys(a.left_rflags + ib, E + 1);
+                else st_release(a.flags + ib, gstep + 1);
+            }
             t_wb += clock64() - c3;
         }
         t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2;
@@ -589,23 +695,30 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
 // preparation kernels: cell key -> stable sort -> per-cell greedy edge colouring -> wave tables
 // ------------------------------------------------------------------------------------------------
 __global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int B, int C,
-                                int n_users, int n_items, unsigned* __restrict__ key, int* __restrict__ val,
-                                int* __restrict__ cnt, int* status) {
+                                int P, int rank, int n_users, int n_items, unsigned n_cells, unsigned* __restrict__ key,
+                                int* __restrict__ val, int* __restrict__ cnt, int* status) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int uu = u[k], ii = i[k];
     val[k] = (int)k;
     if (uu < 0 || uu >= n_users || ii < 0 || ii >= n_items) {
         atomicExch(status, 1);
-        key[k] = 0;
+        key[k] = n_cells;
         return;
     }
-    const int ub = uu % B, ibk = ii % B;
+    // ring over P ranks: this rank keeps the ratings of its own users (u % P == rank); the others sort behind
+    // the last cell.  Local ids: user u / P, item i / P inside super-block i % P, visited in sub-epoch S.
+    if (uu % P != rank) {
+        key[k] = n_cells;
+        return;
+    }
+    const int S = ((ii % P) - rank + P) % P;
+    const int ub = (uu / P) % B, ibk = (ii / P) % B;
     // stratum of the two-level ring: outer step T moves super-blocks between clusters, inner step t inside
     const int K = B / C;
     const int Cl = ub / C, c = ub % C, D = ibk / C, j = ibk % C;
     const int T = (D - Cl + K) % K, t = (j - c + C) % C;
-    const int s = T * C + t;
+    const int s = S * B + T * C + t;
     const unsigned cell = (unsigned)(s * B + ub);
     key[k] = cell;
     atomicAdd(&cnt[cell], 1);
@@ -614,7 +727,7 @@ __global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const 
 // One warp per cell.  Lane 0 walks the cell's ratings in their (stable) input order and gives each the
 // lowest colour not yet used by its user or its item (64-bit masks in shared memory); colours >= 63
 // share the sequential tail.  Then a counting sort by colour writes the records and the wave table.
-__global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int max_ul, int max_il,
+__global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int P, int max_ul, int max_il,
                                                         const int* __restrict__ cell_off, const int* __restrict__ val,
                                                         const int32_t* __restrict__ u, const int32_t* __restrict__ i,
                                                         const double* __restrict__ r, uint8_t* __restrict__ color_tmp,
@@ -633,7 +746,7 @@ __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int 
             atomicMax(&status[1], k1 - k0);
             for (int k = k0; k < k1; ++k) {
                 const int src = val[k];
-                const int ul = u[src] / B, il = i[src] / B;
+                const int ul = (u[src] / P) / B, il = (i[src] / P) / B;
                 const unsigned long long used = masks[ul] | masks[max_ul + il];
                 int c = __ffsll((long long)~used) - 1;  // lowest free colour, -1 if none
                 if (c < 0 || c >= NW - 1) c = NW - 1;
@@ -650,8 +763,8 @@ __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int 
                 const int src = val[k];
                 const int c = color_tmp[k];
                 const int pos = k0 + hist[c]++;
-                ul_out[pos] = u[src] / B;
-                il_out[pos] = i[src] / B;
+                ul_out[pos] = (u[src] / P) / B;
+                il_out[pos] = (i[src] / P) / B;
                 r_out[pos] = (float)r[src];
             }
         }
@@ -659,13 +772,15 @@ __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int 
     }
 }
 
-// fp64 (rows x f) -> fp32 rows of `stride` floats: [0, f) = src, [f, stride) = 0
-__global__ void f64_to_rows_kernel(int64_t rows, int f, int stride, const double* __restrict__ src, float* __restrict__ dst) {
+// fp64 (rows x f) -> fp32 rows of `stride` floats: [0, f) = src, [f, stride) = 0; local row l <- source row
+// first + l * step (ring: the rows of one rank / super-block)
+__global__ void f64_to_rows_kernel(int64_t rows, int f, int stride, const double* __restrict__ src, float* __restrict__ dst,
+                                   int64_t first, int64_t step) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= rows * stride) return;
     const int64_t row = t / stride;
     const int c = (int)(t % stride);
-    dst[t] = c < f ? (float)src[row * f + c] : 0.f;
+    dst[t] = c < f ? (float)src[(first + row * step) * f + c] : 0.f;
 }
 
 // ---- SVD++ companions of the stratified kernel --------------------------------------------------
@@ -693,6 +808,16 @@ __global__ void svdpp_user_refresh_kernel(int64_t n_users, int FP, const int64_t
 // y_j <- y_j d^{c_j} + lr (1 - d^{c_j}) / (c_j (1 - d)) sum_{u in U_j} g_u,  d = 1 - lr reg,  c_j = sum_{u in U_j} cnt_u: what the reference's
 // per-rating updates y_j += lr (err q / sqrt|I_u| - reg y_j) (matrix_factorization.pyx:496-498) add up
 // to over the ratings processed since the last application, with the decay applied exactly.
+// The c decays and the gradient instalments interleave in the reference; with the instalments spread evenly over
+// the c events their decayed sum is acc / c * sum_{k<c} d^k = acc * (1 - d^c) / (c (1 - d)).  For a popular item
+// c * lr * reg >> 1 within one epoch, and the undamped sum overshoots several-fold.
+__device__ __forceinline__ void svdpp_decay_gain(float c, float lr, float reg, float* decay, float* gain) {
+    const float lg = c * log1pf(-lr * reg);
+    *decay = expf(lg);
+    const float x = c * lr * reg;
+    *gain = x > 0.f ? lr * (-expm1f(lg)) / x : lr;  // reg == 0: no decay, plain sum
+}
+
 __global__ void svdpp_item_apply_kernel(int64_t n_items, int FP, const int64_t* __restrict__ i_ptr,
                                         const int32_t* __restrict__ iu_idx, const float* __restrict__ urows,
                                         const float* __restrict__ cnt, float lr, float reg, float* __restrict__ yj) {
@@ -705,18 +830,48 @@ __global__ void svdpp_item_apply_kernel(int64_t n_items, int FP, const int64_t* 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if (c == 0.f) return;
-    // the c decays and the gradient instalments interleave in the reference; with the instalments spread
-    // evenly over the c events their decayed sum is acc / c * sum_{k<c} d^k = acc * (1 - d^c) / (c (1 - d)).
-    // For a popular item c * lr * reg >> 1 within one chunk, and the undamped sum overshoots several-fold.
-    const float lg = c * log1pf(-lr * reg);
-    const float decay = expf(lg);
-    const float x = c * lr * reg;
-    const float gain = x > 0.f ? lr * (-expm1f(lg)) / x : lr;  // reg == 0: no decay, plain sum
+    float decay, gain;
+    svdpp_decay_gain(c, lr, reg, &decay, &gain);
     for (int col = lane; col < FP; col += 32) {
         float acc = 0.f;
         for (int64_t a = b; a < e; ++a) acc += urows[(size_t)iu_idx[a] * 3 * FP + 2 * FP + col];
         yj[(size_t)j * FP + col] = yj[(size_t)j * FP + col] * decay + gain * acc;
     }
+}
+
+// Ring over P ranks: every rank holds the raters of item j that it owns, so the two sums of the application are
+// split -- this kernel writes the rank's partial [sum g_u | sum cnt_u] per item into xch (n_items x (FP + 1)), the
+// host all-reduces xch over the ranks (NCCL), svdpp_item_apply_xch_kernel finishes.  y_j is replicated.
+__global__ void svdpp_item_partial_kernel(int64_t n_items, int FP, const int64_t* __restrict__ i_ptr,
+                                          const int32_t* __restrict__ iu_idx, const float* __restrict__ urows,
+                                          const float* __restrict__ cnt, float* __restrict__ xch) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (j >= n_items) return;
+    const int64_t b = i_ptr[j], e = i_ptr[j + 1];
+    float c = 0.f;
+    for (int64_t a = b + lane; a < e; a += 32) c += cnt[iu_idx[a]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    float* out = xch + (size_t)j * (FP + 1);
+    for (int col = lane; col < FP; col += 32) {
+        float acc = 0.f;
+        for (int64_t a = b; a < e; ++a) acc += urows[(size_t)iu_idx[a] * 3 * FP + 2 * FP + col];
+        out[col] = acc;
+    }
+    if (lane == 0) out[FP] = c;
+}
+__global__ void svdpp_item_apply_xch_kernel(int64_t n_items, int FP, const float* __restrict__ xch, float lr, float reg,
+                                            float* __restrict__ yj) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_items * FP) return;
+    const int64_t j = t / FP;
+    const int col = (int)(t - j * FP);
+    const float c = xch[(size_t)j * (FP + 1) + FP];
+    if (c == 0.f) return;
+    float decay, gain;
+    svdpp_decay_gain(c, lr, reg, &decay, &gain);
+    yj[t] = yj[t] * decay + gain * xch[(size_t)j * (FP + 1) + col];
 }
 
 __global__ void svdpp_isq_kernel(int64_t n_users, const int64_t* __restrict__ u_ptr, float* __restrict__ isq) {
@@ -726,21 +881,41 @@ __global__ void svdpp_isq_kernel(int64_t n_users, const int64_t* __restrict__ u_
         isq[u] = n > 0 ? (float)(1.0 / sqrt(n)) : 0.f;
     }
 }
-__global__ void svdpp_item_count_kernel(int64_t n, const int32_t* __restrict__ i, unsigned long long* cnt, int* max_cnt) {
+// item -> raters CSR of THIS rank's users: key = item id for the ratings of users u % P == rank, n_items (sorts last)
+// for the others; counts per item
+__global__ void svdpp_item_key_kernel(int64_t n, const int32_t* __restrict__ u, const int32_t* __restrict__ i, int P,
+                                      int rank, int n_items, int* __restrict__ key, int* __restrict__ perm,
+                                      unsigned long long* cnt) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < n) {
-        const unsigned long long c = atomicAdd(&cnt[i[k]], 1ull) + 1;
-        atomicMax(max_cnt, (int)c);
+    if (k >= n) return;
+    perm[k] = (int)k;
+    if (u[k] % P != rank) {
+        key[k] = n_items;
+        return;
     }
+    key[k] = i[k];
+    atomicAdd(&cnt[i[k]], 1ull);
 }
-__global__ void svdpp_iota_kernel(int64_t n, int* v) {
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < n) v[k] = (int)k;
-}
-__global__ void svdpp_gather_users_kernel(int64_t n, const int* __restrict__ perm, const int32_t* __restrict__ u,
+__global__ void svdpp_gather_users_kernel(int64_t n, const int* __restrict__ perm, const int32_t* __restrict__ u, int P,
                                           int32_t* __restrict__ out) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < n) out[k] = u[perm[k]];
+    if (k < n) out[k] = u[perm[k]] / P;
+}
+// ur CSR of the rank's users (local user l = global user rank + l P) cut out of the global ur CSR
+__global__ void ring_user_len_kernel(int64_t nu_loc, int P, int rank, const int64_t* __restrict__ u_ptr,
+                                     int64_t* __restrict__ len) {
+    const int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (l < nu_loc) len[l] = u_ptr[rank + l * P + 1] - u_ptr[rank + l * P];
+    if (l == nu_loc) len[l] = 0;
+}
+__global__ void ring_user_copy_kernel(int64_t nu_loc, int P, int rank, const int64_t* __restrict__ u_ptr,
+                                      const int32_t* __restrict__ ui_idx, const int64_t* __restrict__ loc_ptr,
+                                      int32_t* __restrict__ loc_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t l = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (l >= nu_loc) return;
+    const int64_t src = u_ptr[rank + l * P], dst = loc_ptr[l], len = loc_ptr[l + 1] - dst;
+    for (int64_t a = lane; a < len; a += 32) loc_idx[dst + a] = ui_idx[src + a];
 }
 __global__ void rows_to_f64_kernel(int64_t rows, int f, int stride, const float* __restrict__ src, double* __restrict__ dst) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -760,16 +935,19 @@ __global__ void f32_to_f64_kernel(int64_t n, const float* __restrict__ src, doub
 // plan object (C-ABI handle)
 // ------------------------------------------------------------------------------------------------
 struct sb2_svd_plan {
-    int64_t n_users = 0, n_items = 0, n = 0;
+    int64_t n_users = 0, n_items = 0, n = 0;  // the GLOBAL shape
+    // ring over P ranks (P == 1: one GPU): this rank owns users u % P == rank (nu_loc of them) and starts with item
+    // super-block `rank`; ni_max = rows of the largest super-block
+    int P = 1, rank = 0, device = 0;
+    int64_t nu_loc = 0, ni_max = 0, n_loc = 0;
     sb2_sgd_params prm;
     int B = 0, W = 0, G = 0, CH = 0, FP = 0;  // W lane-groups of G lanes, CH 128-bit chunks per lane (0: strided)
     bool stage_u = false, stage_i = false, fast = true;
     size_t smem = 0;
-    int *ul = nullptr, *il = nullptr, *off = nullptr, *wave_off = nullptr, *flags = nullptr;
+    int *ul = nullptr, *il = nullptr, *off = nullptr, *wave_off = nullptr, *flags = nullptr, *status = nullptr;
     int rec_cap = 0, max_cell = 0;
     int C = 1, ibuf = 0;  // cluster size, floats per item buffer
     float *r = nullptr, *pu = nullptr, *qi = nullptr, *bu = nullptr, *bi = nullptr;
-    bool owns_factors = true;
     // SVD++ state
     bool with_yj = false;
     int US = 0, chunks = 1;
@@ -778,6 +956,22 @@ struct sb2_svd_plan {
     int32_t *ui_idx = nullptr, *iu_idx = nullptr;
     cudaStream_t alloc_stream = nullptr;
     long long* prof = nullptr;
+    // ring state (P > 1): one cudaMalloc'd slab (exportable with cudaIpcGetMemHandle), same layout on every rank:
+    // [qi: 2 x ni_max x FP | bi: 2 x ni_max | rflags: B | credit: B]
+    void* slab = nullptr;
+    size_t slab_bytes = 0;
+    void *left_slab = nullptr, *right_slab = nullptr;
+    bool left_ipc = false, right_ipc = false;
+    int E_done = 0;  // sub-epochs run since the last reset
+
+    int64_t ni_of(int sb) const { return (n_items - sb + P - 1) / P; }
+    size_t slab_qi_floats() const { return (size_t)ni_max * FP; }
+    float* slab_qi(void* base, int par) const { return reinterpret_cast<float*>(base) + (size_t)par * slab_qi_floats(); }
+    float* slab_bi(void* base, int par) const {
+        return reinterpret_cast<float*>(base) + 2 * slab_qi_floats() + (size_t)par * ni_max;
+    }
+    int* slab_rflags(void* base) const { return reinterpret_cast<int*>(slab_bi(base, 0) + 2 * (size_t)ni_max); }
+    int* slab_credit(void* base) const { return slab_rflags(base) + B; }
 };
 
 namespace sb2 {
@@ -827,7 +1021,9 @@ static void dsgd_launch_config(const sb2_svd_plan* p, int n_blocks, cudaLaunchCo
     // Every CTA must be resident: they wait on each other.  Without clusters the cooperative-launch attribute
     // guarantees it.  With clusters the grid is capped at cudaOccupancyMaxActiveClusters instead: the combination
     // cooperative + cluster launch fails under Nsight Compute (LaunchFailed), and a kernel that cannot be
-    // profiled is not acceptable here.  SB2_DSGD_COOP=1 forces the attribute for cluster launches too.
+    // profiled is not acceptable here; SB2_DSGD_COOP=1 forces the attribute for cluster launches too.  If the SMs
+    // are not free after all (another persistent kernel, an MPS peer), the bounded waits of the kernel (SpinGuard)
+    // turn the would-be hang into SB2_ERR_CUDA.
     if (p->C == 1 || getenv("SB2_DSGD_COOP") != nullptr) {
         attr[na].id = cudaLaunchAttributeCooperative;
         attr[na].val.cooperative = 1;
@@ -865,17 +1061,24 @@ static void plan_free(sb2_svd_plan* p) {
     if (!p) return;
     cudaStream_t st = p->alloc_stream;
     free_async(p->ul, st); free_async(p->il, st); free_async(p->off, st); free_async(p->wave_off, st); free_async(p->flags, st);
-    free_async(p->r, st); free_async(p->prof, st);
+    free_async(p->r, st); free_async(p->prof, st); free_async(p->status, st);
     free_async(p->yj, st); free_async(p->isq, st); free_async(p->cnt, st); free_async(p->u_ptr, st);
     free_async(p->i_ptr, st); free_async(p->ui_idx, st); free_async(p->iu_idx, st);
-    if (p->owns_factors) { free_async(p->pu, st); free_async(p->qi, st); free_async(p->bu, st); free_async(p->bi, st); }
+    free_async(p->pu, st); free_async(p->qi, st); free_async(p->bu, st); free_async(p->bi, st);
+    if (p->left_ipc && p->left_slab) cudaIpcCloseMemHandle(p->left_slab);
+    if (p->right_ipc && p->right_slab && p->right_slab != p->left_slab) cudaIpcCloseMemHandle(p->right_slab);
+    if (p->slab) {
+        cudaStreamSynchronize(st);
+        cudaFree(p->slab);
+    }
     delete p;
 }
 
-// u, i, r: DEVICE arrays (all_ratings COO)
+// u, i, r: DEVICE arrays, the all_ratings COO of the WHOLE trainset (every rank of a ring passes the same arrays and
+// keeps the ratings of its own users); u_ptr / ui_idx: the global ur CSR (SVD++ only)
 int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
                         const double* r, const sb2_sgd_params* prm, int with_yj, const int64_t* u_ptr,
-                        const int32_t* ui_idx, cudaStream_t st, sb2_svd_plan** out) {
+                        const int32_t* ui_idx, int rank, int world, cudaStream_t st, sb2_svd_plan** out) {
     if (with_yj && (!u_ptr || !ui_idx)) {
         set_error("svdpp plan: the ur CSR (u_ptr, ui_idx) is required");
         return SB2_ERR_INVALID;
@@ -884,8 +1087,18 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         set_error("svd_plan: invalid shape");
         return SB2_ERR_INVALID;
     }
+    if (world < 1 || rank < 0 || rank >= world || world > n_users || world > n_items) {
+        set_error("svd_plan: invalid rank %d of %d", rank, world);
+        return SB2_ERR_INVALID;
+    }
     sb2_svd_plan* p = new sb2_svd_plan();
     p->n_users = n_users; p->n_items = n_items; p->n = n; p->prm = *prm;
+    p->P = world; p->rank = rank;
+    cudaGetDevice(&p->device);
+    const int P = world;
+    p->nu_loc = (n_users - rank + P - 1) / P;
+    p->ni_max = ceil_div(n_items, P);
+    const int64_t nu_max = ceil_div(n_users, P);  // sizes that must agree on every rank use the per-rank maxima
     p->alloc_stream = st;
     p->with_yj = with_yj != 0;
     const int f = prm->n_factors;
@@ -916,18 +1129,21 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         const int w = atoi(e);
         if (w > 0 && w * p->G <= threads && (w * p->G) % 32 == 0) p->W = w;
     }
-    // Blocks B (= CTAs = strata per epoch) and cluster size C.  With thread-block clusters an item block hops
+    // Blocks B (= CTAs = strata per sub-epoch) and cluster size C.  With thread-block clusters an item block hops
     // CTA -> CTA through distributed shared memory (~1k cycles) and only every C-th hop goes through L2
     // (~8k cycles), so small cells are affordable: B = K * C as large as the co-residency limit allows, but at
     // least ~16 ratings per cell.  Without clusters (C = 1: rows too long for two smem buffers, or tiny inputs)
     // every hop is an L2 hop and bigger cells win: B ~ sqrt(N / (10 W)).
+    // Ring over P ranks: an epoch is P * B strata of (P B)^2 cells, so the chain of strata -- which is what bounds
+    // the fit, not the arithmetic -- keeps its single-GPU length when the ranks share the single-GPU block count:
+    // B ~ B_1 / P (at least 16).  Every rank derives B and C from the global shape alone, so they agree.
     int B = sm_count();
     int C = 1;
-    const int b_rows = (int)std::min<int64_t>(std::min(n_users, n_items), 1 << 20);
+    const int b_rows = (int)std::min<int64_t>(std::min(nu_max, p->ni_max), 1 << 20);
     const size_t budget = 200 * 1024;
     auto plan_smem = [&](int Bc, int Cc, bool* st_i, bool* st_u, size_t* used, int* ibuf) {
-        const int mul = (int)ceil_div(n_users, Bc), mil = (int)ceil_div(n_items, Bc);
-        const size_t fixed = (size_t)(2 * (NW + 1) + 2 * Bc) * 4 + 64;
+        const int mul = (int)ceil_div(nu_max, Bc), mil = (int)ceil_div(p->ni_max, Bc);
+        const size_t fixed = (size_t)(2 * (NW + 1) + 2 * P * Bc) * 4 + 64;
         *ibuf = (int)round_up((int64_t)mil * (p->FP + 1), 4);
         const size_t need_i = (size_t)(Cc > 1 ? 2 : 1) * *ibuf * sizeof(float) + 16;
         const size_t need_u = (size_t)mul * (p->US + 3) * sizeof(float) + 16;
@@ -938,12 +1154,15 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     };
     size_t smem_used = 0;
     int b_lim;
+    bool b_forced = false;
     {
         const int b_cells = std::max(1, (int)sqrt((double)std::max<int64_t>(n, 1) / 16.0));
-        b_lim = std::min(std::min(B, b_rows), b_cells);
+        int b_tot = std::min(B, b_cells);
+        if (P > 1) b_tot = std::max(b_tot / P, std::min(16, b_tot));
+        b_lim = std::min(b_tot, b_rows);
         if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
             const int b = atoi(e);
-            if (b > 0 && b <= sm_count()) b_lim = std::min(b, b_rows);
+            if (b > 0 && b <= sm_count()) { b_lim = std::min(b, b_rows); b_forced = true; }
         }
     }
     // largest cluster size (16 is the non-portable maximum, 7 such clusters are co-resident on a B200) that
@@ -979,21 +1198,22 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     if (!clustered) {
         // no clusters: every hop is an L2 hop (~8k cycles) and bigger cells win: B ~ sqrt(N / (10 W))
         C = 1;
-        const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n, 1) / (10.0 * p->W)));
+        const int b_work = std::max(4, (int)sqrt((double)std::max<int64_t>(n / ((int64_t)P * P), 1) / (10.0 * p->W)));
         B = std::min(std::min(sm_count(), b_rows), b_work);
-        if (const char* e = getenv("SB2_DSGD_BLOCKS")) {
-            const int b = atoi(e);
-            if (b > 0 && b <= sm_count()) B = std::min(b, b_rows);
-        }
+        if (b_forced) B = b_lim;
     }
     if (B < 1) B = 1;
     p->B = B;
     p->C = C;
-    int max_ul = (int)ceil_div(n_users, B), max_il = (int)ceil_div(n_items, B);
+    int max_ul = (int)ceil_div(nu_max, B), max_il = (int)ceil_div(p->ni_max, B);
     plan_smem(B, C, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
-    const size_t n_cells = (size_t)B * B;
+    const size_t n_cells = (size_t)P * B * B;
 
     auto fail = [&](int rc) { plan_free(p); return rc; };
+    if (P > 1 && !p->stage_i) {
+        set_error("svd ring: item blocks of %d rows x %d factors do not fit in shared memory", max_il, f);
+        return fail(SB2_ERR_UNSUPPORTED);
+    }
 #define PLAN_CUDA(expr)                                                                        \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \
@@ -1009,11 +1229,20 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     PLAN_CUDA(cudaMallocAsync(&p->off, (n_cells + 1) * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->wave_off, n_cells * (NW + 1) * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->flags, (size_t)B * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->status, 16, st));
     PLAN_CUDA(cudaMallocAsync(&p->prof, (size_t)B * 8 * 8, st));
-    PLAN_CUDA(cudaMallocAsync(&p->pu, (size_t)n_users * p->US * 4, st));
-    PLAN_CUDA(cudaMallocAsync(&p->qi, (size_t)n_items * p->FP * 4, st));
-    PLAN_CUDA(cudaMallocAsync(&p->bu, (size_t)n_users * 4, st));
-    PLAN_CUDA(cudaMallocAsync(&p->bi, (size_t)n_items * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->pu, (size_t)p->nu_loc * p->US * 4, st));
+    PLAN_CUDA(cudaMallocAsync(&p->bu, (size_t)p->nu_loc * 4, st));
+    PLAN_CUDA(cudaMemsetAsync(p->status, 0, 16, st));
+    PLAN_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)B * 4, st));
+    if (P == 1) {
+        PLAN_CUDA(cudaMallocAsync(&p->qi, (size_t)n_items * p->FP * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->bi, (size_t)n_items * 4, st));
+    } else {
+        p->slab_bytes = (2 * p->slab_qi_floats() + 2 * (size_t)p->ni_max + 2 * (size_t)B) * 4;
+        PLAN_CUDA(cudaMalloc(&p->slab, p->slab_bytes));
+        PLAN_CUDA(cudaMemsetAsync(p->slab, 0, p->slab_bytes, st));
+    }
 
     // stratify: cell key -> stable radix sort -> per-cell colouring + counting sort -> wave tables
     unsigned *key = nullptr, *key2 = nullptr;
@@ -1043,7 +1272,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     PREP_CUDA(cudaMemsetAsync(cnt, 0, (n_cells + 1) * 4, st));
     PREP_CUDA(cudaMemsetAsync(status, 0, 8, st));
     int end_bit = 1;
-    while (((size_t)1 << end_bit) < n_cells) ++end_bit;
+    while (((size_t)1 << end_bit) <= n_cells) ++end_bit;  // keys 0 .. n_cells (n_cells = "not mine / invalid")
     size_t tb1 = 0, tb2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb1, key, key2, val, val2, (int)n, 0, end_bit, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt, p->off, (int)(n_cells + 1), st);
@@ -1057,7 +1286,8 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     }
     if (n > 0) {
         const unsigned nb = (unsigned)ceil_div(n, 256);
-        dsgd_key_kernel<<<nb, 256, 0, st>>>(n, u, i, B, C, (int)n_users, (int)n_items, key, val, cnt, status);
+        dsgd_key_kernel<<<nb, 256, 0, st>>>(n, u, i, B, C, P, rank, (int)n_users, (int)n_items, (unsigned)n_cells, key, val,
+                                            cnt, status);
         launch_counter()++;
         size_t t1 = tb;
         PREP_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t1, key, key2, val, val2, (int)n, 0, end_bit, st));
@@ -1069,12 +1299,14 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     {
         PREP_CUDA(cudaFuncSetAttribute(dsgd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
         const unsigned grid = (unsigned)std::min<size_t>(n_cells, (size_t)sm_count() * 32);
-        dsgd_color_kernel<<<grid, 32, mask_bytes, st>>>((int)n_cells, B, max_ul, max_il, p->off, val2, u, i, r, color_tmp,
-                                                        p->ul, p->il, p->r, p->wave_off, status);
+        dsgd_color_kernel<<<grid, 32, mask_bytes, st>>>((int)n_cells, B, P, max_ul, max_il, p->off, val2, u, i, r,
+                                                        color_tmp, p->ul, p->il, p->r, p->wave_off, status);
         launch_counter()++;
     }
     int status_h[2] = {0, 0};
+    int n_loc = 0;
     PREP_CUDA(cudaMemcpyAsync(status_h, status, 8, cudaMemcpyDeviceToHost, st));
+    PREP_CUDA(cudaMemcpyAsync(&n_loc, p->off + n_cells, 4, cudaMemcpyDeviceToHost, st));
     PREP_CUDA(cudaStreamSynchronize(st));
     PREP_CUDA(cudaGetLastError());
     cleanup();
@@ -1082,26 +1314,25 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         set_error("svd_plan: user / item index out of range");
         return fail(SB2_ERR_INVALID);
     }
+    p->n_loc = n_loc;
     if (p->with_yj) {
-        // ur CSR copy, 1/sqrt|I_u|, ir CSR (item -> raters) for the y_j application, chunk count
+        // ur CSR of this rank's users, 1/sqrt|I_u|, item -> (local) raters CSR for the y_j application
+        const int64_t nu = p->nu_loc;
         PLAN_CUDA(cudaMallocAsync(&p->yj, (size_t)n_items * p->FP * 4, st));
-        PLAN_CUDA(cudaMallocAsync(&p->isq, (size_t)n_users * 4, st));
-        PLAN_CUDA(cudaMallocAsync(&p->cnt, (size_t)n_users * 4, st));
-        PLAN_CUDA(cudaMallocAsync(&p->u_ptr, (size_t)(n_users + 1) * 8, st));
+        PLAN_CUDA(cudaMallocAsync(&p->isq, (size_t)nu * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->cnt, (size_t)nu * 4, st));
+        PLAN_CUDA(cudaMallocAsync(&p->u_ptr, (size_t)(nu + 1) * 8, st));
         PLAN_CUDA(cudaMallocAsync(&p->i_ptr, (size_t)(n_items + 1) * 8, st));
         PLAN_CUDA(cudaMallocAsync(&p->ui_idx, n1 * 4, st));
         PLAN_CUDA(cudaMallocAsync(&p->iu_idx, n1 * 4, st));
-        PLAN_CUDA(cudaMemcpyAsync(p->u_ptr, u_ptr, (size_t)(n_users + 1) * 8, cudaMemcpyDeviceToDevice, st));
-        PLAN_CUDA(cudaMemcpyAsync(p->ui_idx, ui_idx, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        PLAN_CUDA(cudaMemsetAsync(p->cnt, 0, (size_t)n_users * 4, st));
-        svdpp_isq_kernel<<<(unsigned)ceil_div(n_users, 256), 256, 0, st>>>(n_users, p->u_ptr, p->isq);
-        launch_counter()++;
+        PLAN_CUDA(cudaMemsetAsync(p->cnt, 0, (size_t)nu * 4, st));
         unsigned long long* icnt = nullptr;
-        int *maxc = nullptr, *perm_in = nullptr, *perm_out = nullptr, *keys_out = nullptr;
+        int64_t* ulen = nullptr;
+        int *perm_in = nullptr, *perm_out = nullptr, *keys_in = nullptr, *keys_out = nullptr;
         void* tmp2 = nullptr;
         auto cleanup2 = [&]() {
-            free_async(icnt, st); free_async(maxc, st); free_async(perm_in, st); free_async(perm_out, st);
-            free_async(keys_out, st); free_async(tmp2, st);
+            free_async(icnt, st); free_async(ulen, st); free_async(perm_in, st); free_async(perm_out, st);
+            free_async(keys_in, st); free_async(keys_out, st); free_async(tmp2, st);
         };
 #define PP_CUDA(expr)                                                                          \
     do {                                                                                       \
@@ -1113,31 +1344,44 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         }                                                                                      \
     } while (0)
         PP_CUDA(cudaMallocAsync(&icnt, (size_t)(n_items + 1) * 8, st));
-        PP_CUDA(cudaMallocAsync(&maxc, 4, st));
+        PP_CUDA(cudaMallocAsync(&ulen, (size_t)(nu + 1) * 8, st));
         PP_CUDA(cudaMallocAsync(&perm_in, n1 * 4, st));
         PP_CUDA(cudaMallocAsync(&perm_out, n1 * 4, st));
+        PP_CUDA(cudaMallocAsync(&keys_in, n1 * 4, st));
         PP_CUDA(cudaMallocAsync(&keys_out, n1 * 4, st));
         PP_CUDA(cudaMemsetAsync(icnt, 0, (size_t)(n_items + 1) * 8, st));
-        PP_CUDA(cudaMemsetAsync(maxc, 0, 4, st));
-        size_t s1 = 0, s2 = 0;
+        int item_bits = 1;
+        while (((int64_t)1 << item_bits) <= n_items) ++item_bits;
+        size_t s1 = 0, s2 = 0, s3 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, s1, reinterpret_cast<int64_t*>(icnt), p->i_ptr, (int)(n_items + 1), st);
-        cub::DeviceRadixSort::SortPairs(nullptr, s2, i, keys_out, perm_in, perm_out, (int)n, 0, 32, st);
-        const size_t sb = std::max(s1, s2);
+        cub::DeviceRadixSort::SortPairs(nullptr, s2, keys_in, keys_out, perm_in, perm_out, (int)n, 0, item_bits, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, s3, ulen, p->u_ptr, (int)(nu + 1), st);
+        const size_t sb = std::max(std::max(s1, s2), s3);
         PP_CUDA(cudaMallocAsync(&tmp2, sb + 16, st));
+        if (P == 1) {
+            PP_CUDA(cudaMemcpyAsync(p->u_ptr, u_ptr, (size_t)(n_users + 1) * 8, cudaMemcpyDeviceToDevice, st));
+            PP_CUDA(cudaMemcpyAsync(p->ui_idx, ui_idx, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        } else {
+            ring_user_len_kernel<<<(unsigned)ceil_div(nu + 1, 256), 256, 0, st>>>(nu, P, rank, u_ptr, ulen);
+            size_t t5 = sb;
+            PP_CUDA(cub::DeviceScan::ExclusiveSum(tmp2, t5, ulen, p->u_ptr, (int)(nu + 1), st));
+            ring_user_copy_kernel<<<(unsigned)ceil_div(nu * 32, 256), 256, 0, st>>>(nu, P, rank, u_ptr, ui_idx, p->u_ptr,
+                                                                                    p->ui_idx);
+            launch_counter() += 3;
+        }
+        svdpp_isq_kernel<<<(unsigned)ceil_div(nu, 256), 256, 0, st>>>(nu, p->u_ptr, p->isq);
+        launch_counter()++;
         if (n > 0) {
             const unsigned nb = (unsigned)ceil_div(n, 256);
-            svdpp_item_count_kernel<<<nb, 256, 0, st>>>(n, i, icnt, maxc);
-            svdpp_iota_kernel<<<nb, 256, 0, st>>>(n, perm_in);
+            svdpp_item_key_kernel<<<nb, 256, 0, st>>>(n, u, i, P, rank, (int)n_items, keys_in, perm_in, icnt);
             size_t t3 = sb;
-            PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp2, t3, i, keys_out, perm_in, perm_out, (int)n, 0, 32, st));
-            svdpp_gather_users_kernel<<<nb, 256, 0, st>>>(n, perm_out, u, p->iu_idx);
-            launch_counter() += 4;
+            PP_CUDA(cub::DeviceRadixSort::SortPairs(tmp2, t3, keys_in, keys_out, perm_in, perm_out, (int)n, 0, item_bits, st));
+            svdpp_gather_users_kernel<<<nb, 256, 0, st>>>(n, perm_out, u, P, p->iu_idx);
+            launch_counter() += 3;
         }
         size_t t4 = sb;
         PP_CUDA(cub::DeviceScan::ExclusiveSum(tmp2, t4, reinterpret_cast<int64_t*>(icnt), p->i_ptr, (int)(n_items + 1), st));
         launch_counter()++;
-        int max_raters = 0;
-        PP_CUDA(cudaMemcpyAsync(&max_raters, maxc, 4, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
         cleanup2();
         // y_j is applied `chunks` times per epoch.  One application per epoch is the schedule that mirrors the
@@ -1148,11 +1392,10 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         // sequential oracle at the full ml-10M shape (tests/golden/svdpp_oracle_rmse.json): 1 application
         // 0.8381 vs 0.8380; 2..32 applications 0.847..0.866 (the mid-epoch refresh cuts the own-push
         // accumulation short); DESIGN.md "SVD++".
-        (void)max_raters;
         p->chunks = 1;
         if (const char* e = getenv("SB2_SVDPP_CHUNKS")) {
             const int c = atoi(e);
-            if (c >= 1) p->chunks = std::min(c, B);
+            if (c >= 1 && P == 1) p->chunks = std::min(c, B);
         }
     }
     // shared-memory plan: wave table + cell offsets, item buffer(s), user block, then as many of a cell's
@@ -1166,36 +1409,47 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     return SB2_OK;
 }
 
-// pu0 / qi0: DEVICE fp64 (n_users x f), (n_items x f)
+// pu0 / qi0 (/ yj0): DEVICE fp64, the WHOLE (n_users x f), (n_items x f) initial matrices; a rank of a ring keeps
+// its users' rows and the rows of item super-block `rank`.  Ring: this also clears the mailboxes the neighbours
+// write into, so the caller must synchronise the ranks between reset and run (RingSVD: one all-reduce).
 int svd_plan_reset_dev(sb2_svd_plan* p, const double* pu0, const double* qi0, const double* yj0, cudaStream_t st) {
     const int f = p->prm.n_factors;
-    f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_users * p->US, 256), 256, 0, st>>>(p->n_users, f, p->US, pu0, p->pu);
+    const int P = p->P, g = p->rank;
+    f64_to_rows_kernel<<<(unsigned)ceil_div(p->nu_loc * p->US, 256), 256, 0, st>>>(p->nu_loc, f, p->US, pu0, p->pu, g, P);
     SB2_LAUNCH_CHECK();
-    f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, f, p->FP, qi0, p->qi);
-    SB2_LAUNCH_CHECK();
+    if (P == 1) {
+        f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, f, p->FP, qi0, p->qi, 0, 1);
+        SB2_LAUNCH_CHECK();
+        SB2_CUDA(cudaMemsetAsync(p->bi, 0, (size_t)p->n_items * 4, st));
+    } else {
+        SB2_CUDA(cudaMemsetAsync(p->slab, 0, p->slab_bytes, st));
+        const int64_t ni = p->ni_of(g);
+        f64_to_rows_kernel<<<(unsigned)ceil_div(ni * p->FP, 256), 256, 0, st>>>(ni, f, p->FP, qi0, p->slab_qi(p->slab, 0), g, P);
+        SB2_LAUNCH_CHECK();
+    }
     if (p->with_yj) {
         if (!yj0) {
             set_error("svd_plan_reset: yj required for SVD++");
             return SB2_ERR_INVALID;
         }
-        f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, f, p->FP, yj0, p->yj);
+        f64_to_rows_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, f, p->FP, yj0, p->yj, 0, 1);
         SB2_LAUNCH_CHECK();
-        SB2_CUDA(cudaMemsetAsync(p->cnt, 0, (size_t)p->n_users * 4, st));
+        SB2_CUDA(cudaMemsetAsync(p->cnt, 0, (size_t)p->nu_loc * 4, st));
     }
-    SB2_CUDA(cudaMemsetAsync(p->bu, 0, (size_t)p->n_users * 4, st));
-    SB2_CUDA(cudaMemsetAsync(p->bi, 0, (size_t)p->n_items * 4, st));
+    SB2_CUDA(cudaMemsetAsync(p->bu, 0, (size_t)p->nu_loc * 4, st));
+    SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+    SB2_CUDA(cudaMemsetAsync(p->status, 0, 16, st));
+    p->E_done = 0;
     return SB2_OK;
 }
 
-int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
-    if (n_epochs <= 0 || p->n == 0) return SB2_OK;
-    DsgdArgs a;
+static int fill_args(sb2_svd_plan* p, DsgdArgs& a) {
     memset(&a, 0, sizeof(a));
-    a.n_users = (int)p->n_users; a.n_items = (int)p->n_items; a.B = p->B; a.W = p->W;
+    a.n_users = (int)p->nu_loc; a.n_items = (int)p->n_items; a.B = p->B; a.W = p->W;
     a.f = p->prm.n_factors; a.FP = p->FP; a.US = p->US;
-    a.max_ul = (int)ceil_div(p->n_users, p->B); a.max_il = (int)ceil_div(p->n_items, p->B);
+    a.max_ul = (int)ceil_div(ceil_div(p->n_users, p->P), p->B); a.max_il = (int)ceil_div(p->ni_max, p->B);
     a.ul = p->ul; a.il = p->il; a.r = p->r; a.cell_off = p->off; a.wave_off = p->wave_off; a.rec_cap = p->rec_cap;
-    a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags;
+    a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags; a.status = p->status;
     a.isq = p->isq; a.cnt = p->cnt;
     a.C = p->C; a.ibuf = p->ibuf;
     const sb2_sgd_params& q = p->prm;
@@ -1204,6 +1458,38 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     a.reg_bu = (float)q.reg_bu; a.reg_bi = (float)q.reg_bi; a.reg_pu = (float)q.reg_pu; a.reg_qi = (float)q.reg_qi;
     a.lr_yj = (float)q.lr_yj; a.reg_yj = (float)q.reg_yj;
     a.prof = p->prof;
+    a.P = p->P; a.rank = p->rank; a.E_base = p->E_done; a.n_items_glob = (int)p->n_items;
+    if (p->P > 1) {
+        if (!p->left_slab || !p->right_slab) {
+            set_error("svd ring: the neighbours are not connected (sb2_svd_ring_connect_*)");
+            return SB2_ERR_INVALID;
+        }
+        for (int par = 0; par < 2; ++par) {
+            a.ring_qi[par] = p->slab_qi(p->slab, par); a.ring_bi[par] = p->slab_bi(p->slab, par);
+            a.left_qi[par] = p->slab_qi(p->left_slab, par); a.left_bi[par] = p->slab_bi(p->left_slab, par);
+        }
+        a.rflags = p->slab_rflags(p->slab); a.credit = p->slab_credit(p->slab);
+        a.left_rflags = p->slab_rflags(p->left_slab); a.right_credit = p->slab_credit(p->right_slab);
+    }
+    return SB2_OK;
+}
+
+int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
+    if (n_epochs <= 0) return SB2_OK;
+    if (p->n == 0 && p->P == 1) return SB2_OK;
+    DsgdArgs a;
+    SB2_TRY(fill_args(p, a));
+    if (p->P > 1) {
+        // ring: one persistent launch for all epochs; the item blocks travel rank -> rank inside the kernel
+        if (p->with_yj) {
+            set_error("svd ring: SVD++ runs epoch by epoch (sb2_svd_ring_epoch_dev)");
+            return SB2_ERR_INVALID;
+        }
+        a.n_epochs = n_epochs; a.s_begin = 0; a.s_end = p->P * p->B;
+        SB2_TRY(dsgd_launch(p, a, st));
+        p->E_done += n_epochs * p->P;
+        return SB2_OK;
+    }
     if (!p->with_yj) {
         int split = 1;  // SB2_DSGD_SPLIT=n: every epoch as n launches over strata ranges (same updates, same order)
         if (const char* e = getenv("SB2_DSGD_SPLIT")) split = std::max(1, std::min(atoi(e), p->B));
@@ -1242,15 +1528,50 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     return SB2_OK;
 }
 
-// outputs: DEVICE fp64
+// One SVD++ epoch of a ring, in two halves around the caller's all-reduce of xch (n_items x (FP + 1) fp32, DEVICE):
+//   phase 0: refresh z_u of the rank's users from the (replicated) y_j, run the epoch's P sub-epochs, write the
+//            rank's partial [sum_u g_u | sum_u cnt_u] per item into xch;
+//   phase 1: apply the all-reduced xch to y_j (identical on every rank afterwards).
+int svd_ring_epoch_dev(sb2_svd_plan* p, int phase, float* xch, cudaStream_t st) {
+    if (!p->with_yj || !xch) {
+        set_error("svd_ring_epoch: SVD++ plan and exchange buffer required");
+        return SB2_ERR_INVALID;
+    }
+    const float lr = (float)p->prm.lr_yj, reg = (float)p->prm.reg_yj;
+    if (phase == 1) {
+        svdpp_item_apply_xch_kernel<<<(unsigned)ceil_div(p->n_items * p->FP, 256), 256, 0, st>>>(p->n_items, p->FP, xch, lr,
+                                                                                                 reg, p->yj);
+        SB2_LAUNCH_CHECK();
+        return SB2_OK;
+    }
+    DsgdArgs a;
+    SB2_TRY(fill_args(p, a));
+    svdpp_user_refresh_kernel<<<(unsigned)ceil_div(p->nu_loc * 32, 256), 256, 0, st>>>(p->nu_loc, p->FP, p->u_ptr, p->ui_idx,
+                                                                                       p->yj, p->isq, p->pu, p->cnt);
+    SB2_LAUNCH_CHECK();
+    a.n_epochs = 1; a.s_begin = 0; a.s_end = p->P * p->B;
+    if (p->P == 1) SB2_CUDA(cudaMemsetAsync(p->flags, 0, (size_t)p->B * 4, st));
+    SB2_TRY(dsgd_launch(p, a, st));
+    p->E_done += p->P;
+    svdpp_item_partial_kernel<<<(unsigned)ceil_div(p->n_items * 32, 256), 256, 0, st>>>(p->n_items, p->FP, p->i_ptr,
+                                                                                        p->iu_idx, p->pu, p->cnt, xch);
+    SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+// outputs: DEVICE fp64.  Ring: the rank's own rows -- users rank, rank + P, .. and the items of super-block `rank`
+// (home again after whole epochs) -- in local order; y_j whole.
 int svd_plan_read_dev(sb2_svd_plan* p, double* pu, double* qi, double* bu, double* bi, double* yj, cudaStream_t st) {
     const int f = p->prm.n_factors;
+    const int64_t ni = p->P > 1 ? p->ni_of(p->rank) : p->n_items;
+    const float* qsrc = p->P > 1 ? p->slab_qi(p->slab, p->E_done & 1) : p->qi;
+    const float* bsrc = p->P > 1 ? p->slab_bi(p->slab, p->E_done & 1) : p->bi;
     if (pu) {
-        rows_to_f64_kernel<<<(unsigned)ceil_div(p->n_users * f, 256), 256, 0, st>>>(p->n_users, f, p->US, p->pu, pu);
+        rows_to_f64_kernel<<<(unsigned)ceil_div(p->nu_loc * f, 256), 256, 0, st>>>(p->nu_loc, f, p->US, p->pu, pu);
         SB2_LAUNCH_CHECK();
     }
     if (qi) {
-        rows_to_f64_kernel<<<(unsigned)ceil_div(p->n_items * f, 256), 256, 0, st>>>(p->n_items, f, p->FP, p->qi, qi);
+        rows_to_f64_kernel<<<(unsigned)ceil_div(ni * f, 256), 256, 0, st>>>(ni, f, p->FP, qsrc, qi);
         SB2_LAUNCH_CHECK();
     }
     if (yj && p->with_yj) {
@@ -1258,28 +1579,89 @@ int svd_plan_read_dev(sb2_svd_plan* p, double* pu, double* qi, double* bu, doubl
         SB2_LAUNCH_CHECK();
     }
     if (bu) {
-        f32_to_f64_kernel<<<(unsigned)ceil_div(p->n_users, 256), 256, 0, st>>>(p->n_users, p->bu, bu);
+        f32_to_f64_kernel<<<(unsigned)ceil_div(p->nu_loc, 256), 256, 0, st>>>(p->nu_loc, p->bu, bu);
         SB2_LAUNCH_CHECK();
     }
     if (bi) {
-        f32_to_f64_kernel<<<(unsigned)ceil_div(p->n_items, 256), 256, 0, st>>>(p->n_items, p->bi, bi);
+        f32_to_f64_kernel<<<(unsigned)ceil_div(ni, 256), 256, 0, st>>>(ni, bsrc, bi);
         SB2_LAUNCH_CHECK();
     }
     return SB2_OK;
 }
 
-void svd_plan_destroy(sb2_svd_plan* p) { plan_free(p); }
-// Use caller-owned fp32 factor buffers (rows x FP, FP = n_factors rounded up to 4): the multi-GPU ring
-// keeps one user block and a rotating item block per rank in torch tensors and binds them per sub-epoch.
-void svd_plan_bind(sb2_svd_plan* p, float* pu, float* qi, float* bu, float* bi) {
-    if (p->owns_factors) {
-        free_async(p->pu, p->alloc_stream); free_async(p->qi, p->alloc_stream);
-        free_async(p->bu, p->alloc_stream); free_async(p->bi, p->alloc_stream);
+// synchronises the stream; SB2_ERR_CUDA if a wait of the persistent kernel ran into its deadline
+int svd_plan_status(sb2_svd_plan* p, cudaStream_t st) {
+    int h[4] = {0, 0, 0, 0};
+    SB2_CUDA(cudaMemcpyAsync(h, p->status, 16, cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    if (h[0] != 0) {
+        set_error("dsgd kernel: a wait for a neighbour CTA / rank timed out (CTAs not co-resident, or a peer rank "
+                  "is not running); the factors of this fit are invalid");
+        return SB2_ERR_CUDA;
     }
-    p->owns_factors = false;
-    p->pu = pu; p->qi = qi; p->bu = bu; p->bi = bi;
+    return SB2_OK;
 }
-int svd_plan_stride(const sb2_svd_plan* p) { return p->FP; }
+
+void svd_plan_destroy(sb2_svd_plan* p) { plan_free(p); }
+
+// ---- ring plumbing: export / map the neighbours' slabs ---------------------------------------------------------
+int svd_ring_ipc_handle(const sb2_svd_plan* p, unsigned char* out64) {
+    if (!p->slab) {
+        set_error("svd_ring_ipc_handle: not a ring plan (world == 1)");
+        return SB2_ERR_INVALID;
+    }
+    cudaIpcMemHandle_t h;
+    SB2_CUDA(cudaIpcGetMemHandle(&h, p->slab));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out64, &h, 64);
+    return SB2_OK;
+}
+int svd_ring_connect_ipc(sb2_svd_plan* p, const unsigned char* left64, const unsigned char* right64) {
+    if (!p->slab) {
+        set_error("svd_ring_connect: not a ring plan (world == 1)");
+        return SB2_ERR_INVALID;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, left64, 64);
+    SB2_CUDA(cudaIpcOpenMemHandle(&p->left_slab, h, cudaIpcMemLazyEnablePeerAccess));
+    p->left_ipc = true;
+    if (memcmp(left64, right64, 64) == 0) {  // two ranks: both neighbours are the same slab
+        p->right_slab = p->left_slab;
+    } else {
+        memcpy(&h, right64, 64);
+        SB2_CUDA(cudaIpcOpenMemHandle(&p->right_slab, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    p->right_ipc = true;
+    return SB2_OK;
+}
+// neighbours that live in the same process (one process driving several GPUs, or several ranks of a test sharing
+// one GPU on different streams)
+int svd_ring_connect_local(sb2_svd_plan* p, sb2_svd_plan* left, sb2_svd_plan* right) {
+    if (!p->slab || !left->slab || !right->slab || left->B != p->B || right->B != p->B || left->ni_max != p->ni_max) {
+        set_error("svd_ring_connect_local: plans are not ranks of the same ring");
+        return SB2_ERR_INVALID;
+    }
+    for (sb2_svd_plan* q : {left, right})
+        if (q->device != p->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                set_error("cudaDeviceEnablePeerAccess(%d): %s", q->device, cudaGetErrorString(e));
+                return SB2_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+    p->left_slab = left->slab;
+    p->right_slab = right->slab;
+    p->left_ipc = p->right_ipc = false;
+    return SB2_OK;
+}
+void svd_ring_info(const sb2_svd_plan* p, int64_t* nu_loc, int64_t* ni_loc, int64_t* n_loc, int* stride) {
+    if (nu_loc) *nu_loc = p->nu_loc;
+    if (ni_loc) *ni_loc = p->P > 1 ? p->ni_of(p->rank) : p->n_items;
+    if (n_loc) *n_loc = p->n_loc;
+    if (stride) *stride = p->FP;
+}
+
 // cycles spent by each CTA of the last run in {flag wait, block load, updates, write-back}: host array [B][8] (see DsgdArgs::prof)
 int svd_plan_profile(const sb2_svd_plan* p, long long* out_host) {
     SB2_CUDA(cudaMemcpy(out_host, p->prof, (size_t)p->B * 8 * 8, cudaMemcpyDeviceToHost));

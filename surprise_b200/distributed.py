@@ -1,15 +1,17 @@
-"""Multi-GPU stratified SGD for SVD: one process per GPU, item blocks rotating rank -> rank.
+"""Multi-GPU paths (one process per GPU, torch.distributed for the plumbing): SVD / SVD++ ring, row-sharded
+similarity build and k-NN estimates, sharded NMF.
 
-With P ranks, user u belongs to rank u % P (local row u // P) and item i to item super-block i % P
-(local row i // P).  An epoch is P sub-epochs; in sub-epoch S rank g runs the single-GPU stratified
-kernel over the ratings whose user it owns and whose item lies in super-block (g + S) % P, then hands
-that super-block's (qi, bi) rows to rank g - 1 and receives the next one from rank g + 1
-(torch.distributed P2P: NCCL over NVLink on GPUs, gloo in the CPU tests).  The user rows never move.
-This is the rank-level repetition of the CTA-level ring inside the kernel (csrc/sgd.cu).
+SVD / SVD++ (DSGD strata across ranks).  With P ranks, user u belongs to rank u % P (local row u // P) and item i to
+item super-block i % P (local row i // P).  An epoch is P sub-epochs; in sub-epoch E (counted from the start of the
+fit) rank g updates the ratings whose user it owns and whose item lies in super-block (g + E) % P, then that
+super-block's (qi, bi) rows move to rank g - 1.  The user rows never move.  This is the rank-level repetition of
+the CTA-level ring inside the kernel (csrc/sgd.cu) and it runs INSIDE the kernel too: the CTA that finishes an item
+block stores it into the left neighbour's buffer through a peer mapping of that rank's memory (cudaIpc, NVLink) and
+publishes it with a system-scope release flag; the neighbour's CTAs poll their own memory.  One persistent launch
+per rank covers a whole SVD fit (SVD++: one per epoch, around the all-reduce of the per-item y_j sums).
 
-``run_block(sb, pu, bu, qi, bi)`` is the unit of work of one sub-epoch; the product passes a closure
-over sb2_svd_plan_run, the CPU tests pass a host function so that the partitioning / rotation logic is
-covered without a GPU.
+``partition`` / ``ring_epochs`` / ``make_exchange`` below are the HOST MODEL of that schedule: the gloo tests run it
+with the oracle's sequential SGD as the unit of work to pin partitioning and rotation without a GPU.
 """
 import numpy as np
 
@@ -59,94 +61,153 @@ def make_exchange(dist, rank, world, tensors, scratch):
     return exchange
 
 
+def ring_neighbours(rank, world):
+    """(left, right): the rank that receives this rank's item blocks, the rank that delivers them."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def interleave_rows(parts, n_total, world):
+    """parts[p]: the rows p, p + world, p + 2 world, ... (possibly padded at the end) -> the n_total rows in order."""
+    first = parts[0]
+    full = first.new_zeros((n_total,) + tuple(first.shape[1:]))
+    for p in range(world):
+        full[p::world] = parts[p][:local_rows(n_total, p, world)]
+    return full
+
+
+def all_gather_interleaved(dist, local, n_total, rank, world):
+    """Every rank contributes its rows (rank, rank + world, ...) of an n_total-row array; returns all rows in order."""
+    import torch
+    if world == 1:
+        return local
+    n_max = local_rows(n_total, 0, world)
+    pad = local.new_zeros((n_max,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return interleave_rows(parts, n_total, world)
+
+
 class RingSVD(object):
-    """SVD fit sharded over the ranks of an initialised torch.distributed group (see module docstring).
+    """SVD / SVD++ fit sharded over the ranks of an initialised torch.distributed group (module docstring).
 
-    u, i, r: the all_ratings() COO on the host (every rank passes the same arrays); prm: _native.SgdParams.
-    world == 1 degenerates to the single-GPU plan."""
+    u, i, r: the all_ratings() COO (host arrays or CUDA tensors; every rank passes the same data and keeps the
+    ratings of its own users); prm: _native.SgdParams; ur_csr = (u_ptr, ui_idx) makes it SVD++.
+    dist=None (or world 1) degenerates to the single-GPU plan.  Collective: every rank must construct, reset,
+    run, gather and close together."""
 
-    def __init__(self, dist, u, i, r, n_users, n_items, prm):
+    def __init__(self, dist, u, i, r, n_users, n_items, prm, ur_csr=None):
         import ctypes as C
         from . import _native as nat
         self.nat, self.C, self.dist = nat, C, dist
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
-        self.n_users, self.n_items, self.prm = n_users, n_items, prm
+        self.n_users, self.n_items, self.prm = int(n_users), int(n_items), prm
         self.f = prm.n_factors
-        P, g = self.world, self.rank
-        self.nu_loc = local_rows(n_users, g, P)
-        self.ni_loc = [local_rows(n_items, sb, P) for sb in range(P)]
-        self.n_local = 0
-        self.plans = []
-        for sb, (ul, il, rl) in enumerate(partition(np.asarray(u), np.asarray(i), np.asarray(r), g, P)):
-            ul, il = np.ascontiguousarray(ul), np.ascontiguousarray(il)
-            rl = np.ascontiguousarray(rl, dtype=np.float64)
-            plan = C.c_void_p()
-            nat.check(nat.lib().sb2_svd_plan_create(self.nu_loc, self.ni_loc[sb], len(rl), nat.hptr(ul), nat.hptr(il),
-                                                    nat.hptr(rl), C.byref(prm), 0, C.byref(plan)))
-            self.plans.append(plan)
-            self.n_local += len(rl)
-        torch = nat.torch_cuda()
-        self.FP = nat.lib().sb2_svd_plan_stride(self.plans[0])
-        dev = nat.device()
-        ni_max = max(self.ni_loc)
-        self.pu = torch.zeros((self.nu_loc, self.FP), dtype=torch.float32, device=dev)
-        self.bu = torch.zeros((self.nu_loc,), dtype=torch.float32, device=dev)
-        self.qi = torch.zeros((ni_max, self.FP), dtype=torch.float32, device=dev)
-        self.bi = torch.zeros((ni_max,), dtype=torch.float32, device=dev)
-        self._scratch = (torch.zeros_like(self.qi), torch.zeros_like(self.bi))
-        self._exchange = (make_exchange(dist, g, P, (self.qi, self.bi), self._scratch) if P > 1 else (lambda: None))
-        self.held = g
-
-    def reset(self, pu0, qi0):
-        """pu0 / qi0: full float64 host (or device) init matrices; each rank keeps its rows."""
-        torch = self.nat.torch_cuda()
-        P, g = self.world, self.rank
-        pu0 = torch.as_tensor(pu0)[g::P].to(self.pu.device, dtype=torch.float32)
-        qi0 = torch.as_tensor(qi0)[g::P].to(self.pu.device, dtype=torch.float32)
-        self.pu.zero_(); self.qi.zero_(); self.bu.zero_(); self.bi.zero_()
-        self.pu[:, :self.f] = pu0
-        self.qi[:qi0.shape[0], :self.f] = qi0
-        self.held = g
-
-    def _run_block(self, sb):
-        nat = self.nat
+        self.with_yj = ur_csr is not None
         lib = nat.lib()
-        nat.check(lib.sb2_svd_plan_bind_dev(self.plans[sb], nat.ptr(self.pu), nat.ptr(self.qi), nat.ptr(self.bu),
-                                            nat.ptr(self.bi)))
-        nat.check(lib.sb2_svd_plan_run(self.plans[sb], 1, nat.stream()))
+        torch = nat.torch_cuda()
+        d_u, d_i, d_r = nat.to_dev(u, np.int32), nat.to_dev(i, np.int32), nat.to_dev(r, np.float64)
+        d_up = d_ui = None
+        if self.with_yj:
+            d_up, d_ui = nat.to_dev(ur_csr[0], np.int64), nat.to_dev(ur_csr[1], np.int32)
+        self.plan = C.c_void_p()
+        nat.check(lib.sb2_svd_ring_create_dev(self.n_users, self.n_items, int(d_r.shape[0]), nat.ptr(d_u), nat.ptr(d_i),
+                                              nat.ptr(d_r), C.byref(prm), int(self.with_yj), nat.ptr(d_up), nat.ptr(d_ui),
+                                              self.rank, self.world, nat.stream(), C.byref(self.plan)))
+        nu, ni, nl, stride = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        lib.sb2_svd_ring_info(self.plan, C.byref(nu), C.byref(ni), C.byref(nl), C.byref(stride))
+        self.nu_loc, self.ni_loc, self.n_local, self.stride = nu.value, ni.value, nl.value, stride.value
+        self._sync = torch.zeros(1, dtype=torch.int32, device=nat.device())
+        self._xch = (torch.empty((self.n_items, self.stride + 1), dtype=torch.float32, device=nat.device())
+                     if self.with_yj else None)
+        if self.world > 1:
+            mine = (C.c_ubyte * 64)()
+            nat.check(lib.sb2_svd_ring_ipc_handle(self.plan, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine))
+            left, right = ring_neighbours(self.rank, self.world)
+            nat.check(lib.sb2_svd_ring_connect_ipc(self.plan, (C.c_ubyte * 64).from_buffer_copy(handles[left]),
+                                                   (C.c_ubyte * 64).from_buffer_copy(handles[right])))
+
+    def _rendezvous(self):
+        """Stream-ordered meeting point of the ranks (a 4-byte all-reduce): everything every rank enqueued before
+        it has completed on its device before anything enqueued after it starts anywhere."""
+        if self.world > 1:
+            self.dist.all_reduce(self._sync)
+
+    def reset(self, pu0, qi0, yj0=None):
+        """pu0 / qi0 (/ yj0): the WHOLE float64 initial matrices (host or device); each rank keeps its rows."""
+        nat = self.nat
+        d_pu, d_qi = nat.to_dev(pu0, np.float64), nat.to_dev(qi0, np.float64)
+        d_yj = nat.to_dev(yj0, np.float64) if self.with_yj else None
+        self._rendezvous()   # nobody clears its mailboxes while a neighbour's previous fit is still running
+        nat.check(nat.lib().sb2_svd_plan_reset_dev(self.plan, nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_yj), nat.stream()))
+        self._rendezvous()   # every mailbox is clear before any kernel of the new fit starts
 
     def run(self, n_epochs):
-        self.held = ring_epochs(self.rank, self.world, n_epochs, self.held, self._run_block, self._exchange)
+        nat = self.nat
+        lib = nat.lib()
+        if not self.with_yj:
+            nat.check(lib.sb2_svd_plan_run(self.plan, int(n_epochs), nat.stream()))
+            return
+        for _ in range(int(n_epochs)):
+            nat.check(lib.sb2_svd_ring_epoch_dev(self.plan, 0, nat.ptr(self._xch), nat.stream()))
+            if self.world > 1:
+                self.dist.all_reduce(self._xch)
+            nat.check(lib.sb2_svd_ring_epoch_dev(self.plan, 1, nat.ptr(self._xch), nat.stream()))
+
+    def status(self):
+        """Synchronises; raises NativeError if a wait inside the kernel ran into its deadline."""
+        self.nat.check(self.nat.lib().sb2_svd_plan_status(self.plan, self.nat.stream()))
 
     def gather(self):
-        """Full (pu, qi, bu, bi) float64 numpy arrays on every rank."""
-        torch = self.nat.torch_cuda()
-        P = self.world
-        assert self.held == self.rank
-        ni_max = max(self.ni_loc)
-        nu_max = local_rows(self.n_users, 0, P)
+        """Full (pu, qi, bu, bi[, yj]) float64 numpy arrays on every rank."""
+        nat = self.nat
+        f = self.f
+        pu = nat.empty_dev((self.nu_loc, f), np.float64); qi = nat.empty_dev((self.ni_loc, f), np.float64)
+        bu = nat.empty_dev((self.nu_loc,), np.float64); bi = nat.empty_dev((self.ni_loc,), np.float64)
+        yj = nat.empty_dev((self.n_items, f), np.float64) if self.with_yj else None
+        self._rendezvous()   # the last blocks pushed by the right neighbour have landed
+        nat.check(nat.lib().sb2_svd_plan_read_dev(self.plan, nat.ptr(pu), nat.ptr(qi), nat.ptr(bu), nat.ptr(bi), nat.ptr(yj),
+                                                  nat.stream()))
+        self.status()
         outs = []
-        for t, n_max, n_tot in ((self.pu, nu_max, self.n_users), (self.qi, ni_max, self.n_items),
-                                (self.bu, nu_max, self.n_users), (self.bi, ni_max, self.n_items)):
-            pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            pad[:min(t.shape[0], n_max)] = t[:n_max]
-            if P > 1:
-                parts = [torch.zeros_like(pad) for _ in range(P)]
-                self.dist.all_gather(parts, pad)
-            else:
-                parts = [pad]
-            full = torch.zeros((n_tot,) + tuple(t.shape[1:]), dtype=torch.float64, device=t.device)
-            for p in range(P):
-                rows = local_rows(n_tot, p, P)
-                full[p::P] = parts[p][:rows].double()
-            outs.append(full[..., :self.f].cpu().numpy() if full.dim() == 2 else full.cpu().numpy())
+        for t, n_tot in ((pu, self.n_users), (qi, self.n_items), (bu, self.n_users), (bi, self.n_items)):
+            outs.append(all_gather_interleaved(self.dist, t, n_tot, self.rank, self.world).cpu().numpy())
+        if self.with_yj:
+            outs.append(yj.cpu().numpy())
         return tuple(outs)
 
     def close(self):
-        for p in self.plans:
-            self.nat.lib().sb2_svd_plan_destroy(p)
-        self.plans = []
+        if self.plan:
+            self._rendezvous()   # no neighbour still maps / writes this rank's buffers
+            self.nat.torch_cuda().cuda.synchronize()
+            self.nat.lib().sb2_svd_plan_destroy(self.plan)
+            self.plan = None
+
+
+def fit_sharded(algo, trainset, dist):
+    """algo: a surprise_b200 SVD or SVDpp instance; fits it over the ranks of `dist` (every rank calls this with the
+    same trainset and ends up with the same fitted attributes), so that algo.test() / predict() work as usual.
+    Mirrors algo.fit(trainset) (matrix_factorization.pyx:153-156, :413-418)."""
+    from .prediction_algorithms.algo_base import AlgoBase
+    AlgoBase.fit(algo, trainset)
+    pu0, qi0, yj0 = algo._initial_factors(trainset)
+    u, i, r = trainset.coo()
+    ur = trainset.user_csr()[:2] if yj0 is not None else None
+    ring = RingSVD(dist, u, i, r, trainset.n_users, trainset.n_items, algo._sgd_params(trainset), ur_csr=ur)
+    try:
+        ring.reset(pu0, qi0, yj0)
+        ring.run(algo.n_epochs)
+        out = ring.gather()
+    finally:
+        ring.close()
+    algo.pu, algo.qi, algo.bu, algo.bi = out[:4]
+    if yj0 is not None:
+        algo.yj = out[4]
+    algo._dev_cache = None
+    return algo
 
 
 # ------------------------------------------------------------------------------------------------------------

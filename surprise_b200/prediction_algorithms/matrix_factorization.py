@@ -97,10 +97,18 @@ class SVD(_FactorModel):
                              lr_pu=self.lr_pu, lr_qi=self.lr_qi, lr_yj=lr_yj, reg_bu=self.reg_bu, reg_bi=self.reg_bi,
                              reg_pu=self.reg_pu, reg_qi=self.reg_qi, reg_yj=reg_yj)
 
-    def sgd(self, trainset):
+    def _initial_factors(self, trainset):
+        """(pu, qi, None): rng.normal draws in the reference's order (matrix_factorization.pyx:233-236)."""
         rng = get_rng(self.random_state)
         pu = rng.normal(self.init_mean, self.init_std_dev, (trainset.n_users, self.n_factors))
         qi = rng.normal(self.init_mean, self.init_std_dev, (trainset.n_items, self.n_factors))
+        return pu, qi, None
+
+    def _sgd_params(self, trainset):
+        return self._params(trainset, biased=self.biased)
+
+    def sgd(self, trainset):
+        pu, qi, _ = self._initial_factors(trainset)
         if self.verbose:
             for ep in range(self.n_epochs):
                 print("Processing epoch {}".format(ep))
@@ -108,7 +116,7 @@ class SVD(_FactorModel):
         d_pu, d_qi = nat.to_dev(pu, np.float64), nat.to_dev(qi, np.float64)
         d_bu = nat.empty_dev((trainset.n_users,), np.float64)
         d_bi = nat.empty_dev((trainset.n_items,), np.float64)
-        prm = self._params(trainset, biased=self.biased)
+        prm = self._sgd_params(trainset)
         rc = nat.lib().sb2_svd_fit_dev(trainset.n_users, trainset.n_items, n, nat.ptr(d_u), nat.ptr(d_i), nat.ptr(d_r),
                                        C.byref(prm), nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_bu), nat.ptr(d_bi),
                                        nat.stream())
@@ -147,12 +155,20 @@ class SVDpp(_FactorModel):
         self.sgd(trainset)
         return self
 
-    def sgd(self, trainset):
+    def _initial_factors(self, trainset):
+        """(pu, qi, yj) drawn in the reference's order (matrix_factorization.pyx:455-460)."""
         rng = get_rng(self.random_state)
         shape_u, shape_i = (trainset.n_users, self.n_factors), (trainset.n_items, self.n_factors)
         pu = rng.normal(self.init_mean, self.init_std_dev, shape_u)
         qi = rng.normal(self.init_mean, self.init_std_dev, shape_i)
         yj = rng.normal(self.init_mean, self.init_std_dev, shape_i)
+        return pu, qi, yj
+
+    def _sgd_params(self, trainset):
+        return SVD._params(self, trainset, lr_yj=self.lr_yj, reg_yj=self.reg_yj, biased=True)
+
+    def sgd(self, trainset):
+        pu, qi, yj = self._initial_factors(trainset)
         if self.verbose:
             for ep in range(self.n_epochs):
                 print(" processing epoch {}".format(ep))
@@ -162,7 +178,7 @@ class SVDpp(_FactorModel):
         d_pu, d_qi, d_yj = (nat.to_dev(a, np.float64) for a in (pu, qi, yj))
         d_bu = nat.empty_dev((trainset.n_users,), np.float64)
         d_bi = nat.empty_dev((trainset.n_items,), np.float64)
-        prm = SVD._params(self, trainset, lr_yj=self.lr_yj, reg_yj=self.reg_yj, biased=True)
+        prm = self._sgd_params(trainset)
         rc = nat.lib().sb2_svdpp_fit_dev(trainset.n_users, trainset.n_items, n, nat.ptr(d_u), nat.ptr(d_i),
                                          nat.ptr(d_r), nat.ptr(d_up), nat.ptr(d_ui), C.byref(prm), nat.ptr(d_pu),
                                          nat.ptr(d_qi), nat.ptr(d_yj), nat.ptr(d_bu), nat.ptr(d_bi), nat.stream())

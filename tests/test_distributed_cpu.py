@@ -199,3 +199,49 @@ def test_nmf_all_gather_rows_two_ranks(tmp_path):
     want = np.arange(33, dtype=np.float64).reshape(11, 3)
     for r in range(2):
         assert np.array_equal(np.load(os.path.join(str(tmp_path), "g%d.npy" % r)), want)
+
+
+def _interleave_worker(rank, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=3)
+    n, f = 10, 4                                   # 10 rows over 3 ranks: 4 + 3 + 3 (uneven, padded all-gather)
+    truth = torch.arange(n * f, dtype=torch.float64).reshape(n, f)
+    mine = truth[rank::3].clone()
+    assert mine.shape[0] == D.local_rows(n, rank, 3)
+    full = D.all_gather_interleaved(dist, mine, n, rank, 3)
+    vec = D.all_gather_interleaved(dist, truth[rank::3, 0].clone(), n, rank, 3)
+    handles = [None] * 3
+    dist.all_gather_object(handles, bytes([rank]) * 64)      # the IPC-handle exchange of RingSVD.__init__
+    left, right = D.ring_neighbours(rank, 3)
+    assert handles[left] == bytes([(rank - 1) % 3]) * 64 and handles[right] == bytes([(rank + 1) % 3]) * 64
+    np.savez(os.path.join(out_dir, "i%d.npz" % rank), full=full.numpy(), vec=vec.numpy())
+    dist.destroy_process_group()
+
+
+def test_ring_gather_interleaved_three_ranks(tmp_path):
+    """What RingSVD.gather does with the ranks' own rows (users g, g + P, ...): padded all-gather + interleave."""
+    import torch.multiprocessing as mp
+    port = 37500 + (os.getpid() % 2000)
+    mp.spawn(_interleave_worker, args=(port, str(tmp_path)), nprocs=3, join=True)
+    want = np.arange(40, dtype=np.float64).reshape(10, 4)
+    for r in range(3):
+        got = np.load(os.path.join(str(tmp_path), "i%d.npz" % r))
+        assert np.array_equal(got["full"], want) and np.array_equal(got["vec"], want[:, 0])
+
+
+def test_ring_schedule_model_matches_kernel_formula():
+    """The kernel's schedule: in sub-epoch E rank g holds super-block (g + E) % P and hands it to g - 1; the host model
+    (ring_epochs) must visit the same blocks in the same order and end at home after whole epochs."""
+    for world in (1, 2, 3, 8):
+        for g in range(world):
+            seen = []
+            held = D.ring_epochs(g, world, 2, g, seen.append, lambda: None)
+            assert held == g
+            assert seen == [(g + e) % world for e in range(2 * world)]
+            left, right = D.ring_neighbours(g, world)
+            # the block rank g holds in sub-epoch E is the one its right neighbour held in E - 1
+            assert all((right + e - 1) % world == (g + e) % world for e in range(1, 2 * world))
+            assert (left + 1) % world == g
