@@ -79,6 +79,7 @@ struct PackArgs {
     int na, nc;
     int* status;
     int64_t n_x;
+    int64_t x_min;  // rows below x_min are not read by this build (shard of a symmetric multi-rank build): not packed
     int truncate;
 };
 
@@ -92,6 +93,7 @@ __global__ void sim_pack_kernel(const PackArgs p) {
         atomicExch(&p.status[ST_BAD_RATING], 2);
         return;
     }
+    if (x < p.x_min) return;
     const size_t o = (size_t)x * (size_t)p.k_pad + (size_t)y;
     // mask byte through a word atomic so that a second (x, y) hit is detected
     unsigned* mw = reinterpret_cast<unsigned*>(p.m_panel + (o & ~(size_t)3));
@@ -371,13 +373,22 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
     const int n_panels = 1 + nq + ns + na + nc;
     DevBuf panels_d;
     SB2_TRY(panels_d.alloc(panel_bytes * n_panels, st));
-    SB2_CUDA(cudaMemsetAsync(panels_d.p, 0, panel_bytes * n_panels, st));
     uint8_t* base = panels_d.as<uint8_t>();
+    // a shard of a symmetric build (tiles at or above the block diagonal) reads panel rows >= row_begin only: the last
+    // of 8 ranks clears and packs a quarter of the 56 GB of panels (ml-20M shape) instead of all of them
+    const int64_t x_min = upper ? row_begin : 0;
+    if (x_min == 0) {
+        SB2_CUDA(cudaMemsetAsync(base, 0, panel_bytes * n_panels, st));
+    } else {
+        for (int q = 0; q < n_panels; ++q)
+            SB2_CUDA(cudaMemsetAsync(base + panel_bytes * q + (size_t)x_min * (size_t)k_pad, 0,
+                                     (size_t)(n_pad - x_min) * (size_t)k_pad, st));
+    }
     int pi = 0;
     PackArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.y_ptr = y_ptr; pa.x_idx = x_idx; pa.r = r; pa.nnz = nnz; pa.n_y = n_y; pa.k_pad = k_pad;
-    pa.denom = (double)rating_denom; pa.n_x = n_x; pa.truncate = slope ? 1 : 0;
+    pa.denom = (double)rating_denom; pa.n_x = n_x; pa.x_min = x_min; pa.truncate = slope ? 1 : 0;
     pa.m_panel = base + panel_bytes * (pi++);
     pa.nq = nq; pa.ns = ns; pa.na = na; pa.nc = nc;
     for (int d = 0; d < nq; ++d) pa.q_panel[d] = base + panel_bytes * (pi++);

@@ -272,6 +272,35 @@ def sim_exchange(dist, torch, block, ranges, rank):
         block[:, r0:r1] = buf.t()
 
 
+def upload_inputs_broadcast(dist, kind, n_x, yr, x_biases=None, y_biases=None):
+    """similarities.upload_inputs for a group of ranks: rank 0 copies the rating CSR (and the baselines) to its GPU and
+    the other ranks receive them GPU -> GPU over NCCL ("rating matrix broadcast once"), instead of N
+    processes pushing the same 240 MB (ml-20M shape) through the host's PCIe / pageable staging at the same time.
+    Every rank passes the same host yr (only its sizes are used off rank 0)."""
+    from . import similarities as sims
+    nat = sims.nat
+    torch = nat.torch_cuda()
+    rank = dist.get_rank()
+    pb = kind == "pearson_baseline"
+    if rank == 0:
+        inp = sims.upload_inputs(kind, n_x, yr, x_biases, y_biases)
+        meta = torch.tensor([inp["n_y"], inp["nnz"], inp["denom"]], dtype=torch.int64, device=nat.device())
+    else:
+        meta = torch.zeros(3, dtype=torch.int64, device=nat.device())
+    dist.broadcast(meta, 0)
+    n_y, nnz, denom = (int(v) for v in meta.tolist())
+    if rank != 0:
+        inp = dict(n_x=int(n_x), n_y=n_y, nnz=nnz, denom=denom, ptr=nat.empty_dev((n_y + 1,), np.int64),
+                   idx=nat.empty_dev((nnz,), np.int32), val=nat.empty_dev((nnz,), np.float64),
+                   bx=nat.empty_dev((int(n_x),), np.float64) if pb else None,
+                   by=nat.empty_dev((n_y,), np.float64) if pb else None)
+    elif pb:   # rank 0 may hold longer bias arrays than n_x / n_y: broadcast exactly what the kernels read
+        inp["bx"], inp["by"] = inp["bx"][:int(n_x)].contiguous(), inp["by"][:n_y].contiguous()
+    for k in ("ptr", "idx", "val") + (("bx", "by") if pb else ()):
+        dist.broadcast(inp[k], 0)
+    return inp
+
+
 def sim_build_sharded(dist, kind, n_x, yr, min_support, gather=False, symmetric=True, **kw):
     """Returns (row_begin, row_end, block) with block a CUDA float64 tensor (row_end-row_begin) x n_x; with
     gather=True every rank also receives the full matrix (all_gather over NCCL), returned instead of the block."""
@@ -282,6 +311,8 @@ def sim_build_sharded(dist, kind, n_x, yr, min_support, gather=False, symmetric=
     ranges = sim_tri_ranges(n_x, world) if symmetric else [sim_row_range(n_x, r, world) for r in range(world)]
     b, e = ranges[rank]
     torch = sims.nat.torch_cuda()
+    if world > 1 and kw.get("inputs") is None:
+        kw = dict(kw, inputs=upload_inputs_broadcast(dist, kind, n_x, yr, kw.get("x_biases"), kw.get("y_biases")))
     if e > b:
         block = sims.build_device(kind, n_x, yr, min_support, row_begin=b, row_end=e, upper=symmetric, **kw)
     else:

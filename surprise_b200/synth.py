@@ -33,9 +33,19 @@ def ratings(n_users, n_items, n_ratings, step=1.0, seed=0, holdout=0.1, rank=8, 
     else:
         def draw(k):
             return rng.integers(0, n_users * n_items, k, dtype=np.int64)
-    lin = np.unique(draw(int(n_total * 1.08) + 16))
+    def sorted_unique(a):
+        # == np.unique(a), which numpy 2.3 evaluates ~50x slower than a plain sort for 10^7..10^8 int64 keys
+        a = np.sort(a)
+        if len(a) == 0:
+            return a
+        keep = np.empty(len(a), dtype=bool)
+        keep[0] = True
+        np.not_equal(a[1:], a[:-1], out=keep[1:])
+        return a[keep]
+
+    lin = sorted_unique(draw(int(n_total * 1.08) + 16))
     while len(lin) < n_total:
-        lin = np.unique(np.concatenate((lin, draw(n_total))))
+        lin = sorted_unique(np.concatenate((lin, draw(n_total))))
     lin = rng.permutation(lin)[:n_total]
     u_raw = (lin // n_items).astype(np.int64)
     i_raw = (lin % n_items).astype(np.int64)
@@ -43,13 +53,24 @@ def ratings(n_users, n_items, n_ratings, step=1.0, seed=0, holdout=0.1, rank=8, 
     bi = rng.normal(0, .4, n_items)
     p = rng.normal(0, .35, (n_users, rank))
     q = rng.normal(0, .35, (n_items, rank))
-    r = 3.5 + bu[u_raw] + bi[i_raw] + np.einsum("kf,kf->k", p[u_raw], q[i_raw]) + rng.normal(0, .8, n_total)
+    # planted model, evaluated in slabs of 4M ratings (the gathered factor rows of 10^8 ratings would be 14 GB)
+    r = np.empty(n_total)
+    noise = rng.normal(0, .8, n_total)
+    for b in range(0, n_total, 1 << 22):
+        sl = slice(b, min(n_total, b + (1 << 22)))
+        us, is_ = u_raw[sl], i_raw[sl]
+        r[sl] = 3.5 + bu[us] + bi[is_] + np.einsum("kf,kf->k", p[us], q[is_]) + noise[sl]
+    del noise
     lo = step if step < 1 else 1.0
     r = np.clip(np.round(r / step) * step, lo, 5.0)
 
     def first_appearance(a, n):
-        uniq, first = np.unique(a, return_index=True)
-        order = np.argsort(first, kind="stable")
+        # rank of every id by its first occurrence in `a` (-1: absent).  O(len(a)): with repeated indices a fancy
+        # assignment keeps the LAST value written, so writing the positions back to front leaves the first one
+        first = np.full(n, len(a), dtype=np.int64)
+        first[a[::-1]] = np.arange(len(a) - 1, -1, -1, dtype=np.int64)
+        uniq = np.nonzero(first < len(a))[0]
+        order = np.argsort(first[uniq], kind="stable")
         rank_of = np.full(n, -1, dtype=np.int64)
         rank_of[uniq[order]] = np.arange(len(uniq))
         return rank_of
@@ -65,3 +86,34 @@ def ratings(n_users, n_items, n_ratings, step=1.0, seed=0, holdout=0.1, rank=8, 
 def shaped(name, seed=0, scale=1.0):
     nu, ni, n, step = SHAPES[name]
     return ratings(int(nu * scale), int(ni * scale), int(n * scale * scale), step=step, seed=seed)
+
+
+def shaped_cached(name, seed=0, cache_dir=None, with_coo=False):
+    """shaped(name, seed) through an on-disk cache of the generated arrays (uncompressed .npz under cache_dir): the
+    Netflix shape takes ~40 s to draw and the benchmark needs it once per process and per N.  with_coo=True also
+    caches the all_ratings()-ordered COO (u ascending, file order inside a user: what Trainset.coo() returns).
+    Concurrent callers may race to write; the file is written to a temporary name and renamed."""
+    import os
+    if cache_dir is None:
+        return shaped(name, seed=seed)
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, "%s_seed%d%s.npz" % (name, seed, "_coo" if with_coo else ""))
+    if os.path.exists(path):
+        z = np.load(path)
+        d = dict(train=(z["u"], z["i"], z["r"]), test=(z["tu"], z["ti"], z["tr"]), n_users=int(z["n_users"]),
+                 n_items=int(z["n_items"]))
+        if with_coo:
+            d["coo"] = (z["cu"], z["ci"], z["cr"])
+        return d
+    d = shaped(name, seed=seed)
+    arrays = dict(u=d["train"][0], i=d["train"][1], r=d["train"][2], tu=d["test"][0], ti=d["test"][1], tr=d["test"][2],
+                  n_users=np.int64(d["n_users"]), n_items=np.int64(d["n_items"]))
+    if with_coo:
+        from .trainset import Trainset
+        ts = Trainset.from_coo(d["train"][0], d["train"][1], d["train"][2], d["n_users"], d["n_items"])
+        d["coo"] = tuple(np.ascontiguousarray(a) for a in ts.coo())
+        arrays.update(cu=d["coo"][0], ci=d["coo"][1], cr=d["coo"][2])
+    tmp = path + ".%d.tmp.npz" % os.getpid()
+    np.savez(tmp, **arrays)
+    os.replace(tmp, path)
+    return d
