@@ -47,6 +47,9 @@ struct DsgdArgs {
     const float* r;
     const int* cell_off;                // B*B + 1 offsets into the records, cell = s * B + user_block
     const int* wave_off;                // [B*B][NW + 1] wave boundaries relative to the cell start
+    const int* dep;                     // dependency-driven cells (DEP kernels): per record, the number of earlier
+                                        // records of the cell on the same user row | (same item row) << 16
+    int dep_sync;                       // experiment: how a DEP warp publishes its row versions (see the kernel)
     float* pu;                          // n_users x FP
     float* qi;                          // n_items x FP
     float* bu;
@@ -173,6 +176,15 @@ __device__ __forceinline__ void mbar_wait_cluster(SpinGuard& g, uint64_t* bar, u
 __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_cta_shared(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -370,7 +382,13 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
 // registers, which the ring state alone nearly fills (spills).
 __host__ __device__ constexpr int dsgd_threads(int g) { return g >= 16 ? 512 : 256; }
 
-template <int G, int CH, bool SU, bool SI, bool BIASED, bool PP>
+// DEP (G = 32: one warp per rating): instead of waves separated by block barriers, every warp walks its share of the
+// cell's records (record k -> warp k % n_warps, records in colour order) and starts a rating as soon as the two
+// rows it touches carry exactly the updates that precede it in that order -- per-row version counters in shared
+// memory, ld.acquire / st.release at CTA scope.  Same conflict-freedom and determinism as the waves (every row sees
+// its updates in the same fixed order), but a cell costs its dependency chain (max degree x one update latency)
+// or its work / n_warps, whichever is longer, not (number of waves) x (slowest warp of the wave + barrier).
+template <int G, int CH, bool SU, bool SI, bool BIASED, bool PP, bool DEP = false>
 __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const DsgdArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int B = a.B, W = a.W, FP = a.FP, F4 = a.FP >> 2;
@@ -392,6 +410,8 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
     int* rul_s = coff_s + 2 * a.P * B;        // records: two buffers of rec_cap each
     int* ril_s = rul_s + 2 * a.rec_cap;
     float* rr_s = reinterpret_cast<float*>(ril_s + 2 * a.rec_cap);
+    int* rdep_s = reinterpret_cast<int*>(rr_s + 2 * a.rec_cap);   // DEP: two buffers of rec_cap
+    int* ver_s = rdep_s + (DEP ? 2 * a.rec_cap : 0);              // DEP: [max_ul] user-row + [max_il] item-row versions
 
     // ring mailboxes (clusters): bar_data = "my right neighbour's push has landed in my spare buffer",
     // bar_free = "my left neighbour has finished reading the buffer I am about to overwrite"
@@ -465,9 +485,12 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             cp_async4(rul + x, a.ul + k0 + x);
             cp_async4(ril + x, a.il + k0 + x);
             cp_async4(rr + x, a.r + k0 + x);
+            if (DEP) cp_async4(rdep_s + (size_t)(j & 1) * a.rec_cap + x, a.dep + k0 + x);
         }
-        const int* wsrc = a.wave_off + ((size_t)s * B + ub) * (NW + 1);
-        for (int x = tid; x <= NW; x += nthr) cp_async4(wave + x, wsrc + x);
+        if (!DEP) {
+            const int* wsrc = a.wave_off + ((size_t)s * B + ub) * (NW + 1);
+            for (int x = tid; x <= NW; x += nthr) cp_async4(wave + x, wsrc + x);
+        }
     };
     if (n_steps > 0) prefetch(0);
     const int P = a.P;
@@ -507,6 +530,8 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
         const int k0 = coff_s[2 * sg], cnt = coff_s[2 * sg + 1] - k0;
         const int staged = min(cnt, a.rec_cap);
         cp_async_wait_all();  // this stratum's records (issued during the previous stratum)
+        if (DEP)
+            for (int x = tid; x < a.max_ul + a.max_il; x += nthr) ver_s[x] = 0;
         if (wait_flag && tid == 0) {
             // T > 0 (or one rank): the previous cluster still owns the block; T == 0 of a ring: the right
             // neighbour rank delivers it at the end of ITS previous sub-epoch (system-scope release over NVLink)
@@ -570,6 +595,36 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             fetch(k, valid, ul, il, r);
             update(ul, il, r, valid);
         };
+        if (DEP) {
+            const int* rdep_c = rdep_s + (size_t)(step & 1) * a.rec_cap;
+            int* ver_u = ver_s;
+            int* ver_i = ver_s + a.max_ul;
+            for (int k = gid; k < cnt; k += W) {   // G == 32: gid = warp, W = warps
+                int ul, il, dep;
+                float r;
+                if (k < staged) { ul = rul_c[k]; il = ril_c[k]; r = rr_c[k]; dep = rdep_c[k]; }
+                else { ul = a.ul[k0 + k]; il = a.il[k0 + k]; r = a.r[k0 + k]; dep = a.dep[k0 + k]; }
+                const int nu = dep & 0xFFFF, nv = (dep >> 16) & 0xFFFF;
+                // both rows must carry exactly the updates that precede this rating in the cell's order (every lane
+                // acquires for itself; the addresses are warp-uniform: broadcast reads).  The producers are warps of
+                // this CTA working through earlier records: the earliest unfinished record never waits.
+                while (ld_acquire_cta_shared(ver_u + ul) != nu || ld_acquire_cta_shared(ver_i + il) != nv) { }
+                update(ul, il, r, true);
+                __syncwarp();  // orders the lanes' row stores before lane 0's releases
+                if (gl == 0) {
+                    if (a.dep_sync == 0) {
+                        st_release_cta_shared(ver_u + ul, nu + 1);
+                        st_release_cta_shared(ver_i + il, nv + 1);
+                    } else {
+                        if (a.dep_sync == 1) asm volatile("fence.acq_rel.cta;" ::: "memory");
+                        *reinterpret_cast<volatile int*>(ver_u + ul) = nu + 1;
+                        *reinterpret_cast<volatile int*>(ver_i + il) = nv + 1;
+                    }
+                }
+                ++n_wave;
+            }
+            __syncthreads();
+        } else {
         {
             int wb = wave_c[0], we = wave_c[1];
             int c_ul, c_il;
@@ -612,6 +667,7 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
                     }
                 __syncthreads();
             }
+        }
         }
         const long long c3 = clock64();
         if (!last) {
@@ -726,20 +782,25 @@ __global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const 
 
 // One warp per cell.  Lane 0 walks the cell's ratings in their (stable) input order and gives each the
 // lowest colour not yet used by its user or its item (64-bit masks in shared memory); colours >= 63
-// share the sequential tail.  Then a counting sort by colour writes the records and the wave table.
+// share the sequential tail.  Then a counting sort by colour writes the records and the wave table, and
+// (dep_out != nullptr) each record's dependency counts for the DEP kernels: the number of records on the same
+// user row / item row that precede it in the colour-sorted order.  A proper colour occurs at most once per row, so
+// that is a popcount of the row's final mask below the record's colour; tail records (several per row possible)
+// follow all coloured ones in placement order.
 __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int P, int max_ul, int max_il,
                                                         const int* __restrict__ cell_off, const int* __restrict__ val,
                                                         const int32_t* __restrict__ u, const int32_t* __restrict__ i,
                                                         const double* __restrict__ r, uint8_t* __restrict__ color_tmp,
                                                         int* __restrict__ ul_out, int* __restrict__ il_out,
                                                         float* __restrict__ r_out, int* __restrict__ wave_off,
-                                                        int* status) {
-    extern __shared__ unsigned long long masks[];  // [max_ul] user masks, [max_il] item masks
+                                                        int* __restrict__ dep_out, int* status) {
+    extern __shared__ unsigned long long masks[];  // [max_ul] user masks, [max_il] item masks, then int tail counters
+    int* tail_cnt = reinterpret_cast<int*>(masks + max_ul + max_il);
     __shared__ int hist[NW + 1];
     const int lane = threadIdx.x;
     for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int k0 = cell_off[cell], k1 = cell_off[cell + 1];
-        for (int t = lane; t < max_ul + max_il; t += 32) masks[t] = 0ull;
+        for (int t = lane; t < max_ul + max_il; t += 32) { masks[t] = 0ull; tail_cnt[t] = 0; }
         for (int t = lane; t <= NW; t += 32) hist[t] = 0;
         __syncwarp();
         if (lane == 0) {
@@ -759,14 +820,30 @@ __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int 
             }
             for (int c = 0; c < NW; ++c) hist[c + 1] += hist[c];
             for (int c = 0; c <= NW; ++c) wave_off[(size_t)cell * (NW + 1) + c] = hist[c];
+            int worst = 0;
             for (int k = k0; k < k1; ++k) {
                 const int src = val[k];
                 const int c = color_tmp[k];
                 const int pos = k0 + hist[c]++;
-                ul_out[pos] = (u[src] / P) / B;
-                il_out[pos] = (i[src] / P) / B;
+                const int ul = (u[src] / P) / B, il = (i[src] / P) / B;
+                ul_out[pos] = ul;
+                il_out[pos] = il;
                 r_out[pos] = (float)r[src];
+                if (dep_out != nullptr) {
+                    int nu, nv;
+                    if (c < NW - 1) {
+                        const unsigned long long below = (1ull << c) - 1ull;
+                        nu = __popcll(masks[ul] & below);
+                        nv = __popcll(masks[max_ul + il] & below);
+                    } else {
+                        nu = __popcll(masks[ul]) + tail_cnt[ul]++;
+                        nv = __popcll(masks[max_ul + il]) + tail_cnt[max_ul + il]++;
+                    }
+                    worst = max(worst, max(nu, nv));
+                    dep_out[pos] = (nu & 0xFFFF) | (nv << 16);
+                }
             }
+            if (dep_out != nullptr) atomicMax(&status[2], worst);
         }
         __syncwarp();
     }
@@ -943,8 +1020,10 @@ struct sb2_svd_plan {
     sb2_sgd_params prm;
     int B = 0, W = 0, G = 0, CH = 0, FP = 0;  // W lane-groups of G lanes, CH 128-bit chunks per lane (0: strided)
     bool stage_u = false, stage_i = false, fast = true;
+    bool dep_mode = false;  // dependency-driven cells (one warp per rating, per-row version counters) instead of waves
     size_t smem = 0;
     int *ul = nullptr, *il = nullptr, *off = nullptr, *wave_off = nullptr, *flags = nullptr, *status = nullptr;
+    int* dep = nullptr;
     int rec_cap = 0, max_cell = 0;
     int C = 1, ibuf = 0;  // cluster size, floats per item buffer
     float *r = nullptr, *pu = nullptr, *qi = nullptr, *bu = nullptr, *bi = nullptr;
@@ -1001,6 +1080,12 @@ static bool dsgd_shape_ok(int g, int ch) {
 }
 
 static dsgd_kernel_t dsgd_kernel(const sb2_svd_plan* p) {
+    if (p->dep_mode) {  // G = 32, rows staged, plain SVD
+        const bool b = p->prm.biased != 0;
+        if (p->CH == 1)
+            return b ? dsgd_svd_kernel<32, 1, true, true, true, false, true> : dsgd_svd_kernel<32, 1, true, true, false, false, true>;
+        return b ? dsgd_svd_kernel<32, 2, true, true, true, false, true> : dsgd_svd_kernel<32, 2, true, true, false, false, true>;
+    }
     if (!p->fast) return dsgd_kernel_g<32, 0>(p);
 #define SB2_DSGD_CASE(g, ch) \
     if (p->G == g && p->CH == ch) return dsgd_kernel_g<g, ch>(p);
@@ -1061,7 +1146,7 @@ static void plan_free(sb2_svd_plan* p) {
     if (!p) return;
     cudaStream_t st = p->alloc_stream;
     free_async(p->ul, st); free_async(p->il, st); free_async(p->off, st); free_async(p->wave_off, st); free_async(p->flags, st);
-    free_async(p->r, st); free_async(p->prof, st); free_async(p->status, st);
+    free_async(p->r, st); free_async(p->prof, st); free_async(p->status, st); free_async(p->dep, st);
     free_async(p->yj, st); free_async(p->isq, st); free_async(p->cnt, st); free_async(p->u_ptr, st);
     free_async(p->i_ptr, st); free_async(p->ui_idx, st); free_async(p->iu_idx, st);
     free_async(p->pu, st); free_async(p->qi, st); free_async(p->bu, st); free_async(p->bi, st);
@@ -1110,25 +1195,37 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     // lanes win: with ~13 ratings per wave the critical path is one warp's instruction stream either way, and
     // wider groups only add shuffle steps and warps per scheduler (measured at f = 100: G = 8 / 16 / 32 ->
     // 11.7 / 13.1 / 13.8 ms per fit; f = 20: G = 2 / 4 -> 76 / 87 ms at the ml-10M shape; profiles/r1_summary.md).
-    p->fast = F4 <= 64;
-    p->G = 32;
-    p->CH = 0;
-    if (p->fast) {
-        int g = 1;
-        while (g < 16 && 4 * g < F4) g <<= 1;
-        p->G = g;
-        p->CH = (F4 + g - 1) / g;
-        if (const char* e = getenv("SB2_DSGD_LANES")) {
-            const int ge = atoi(e);
-            if (ge > 0 && dsgd_shape_ok(ge, (F4 + ge - 1) / ge)) { p->G = ge; p->CH = (F4 + ge - 1) / ge; }
+    // SB2_DSGD_DEP=1: dependency-driven cells, one warp per rating (DEP kernels; plain SVD, rows of at most 256
+    // floats).  An experiment that did not pay: a cell then costs its dependency chain or its
+    // work / n_warps instead of (waves) x (slowest warp + barrier), but one rating on one warp still takes ~0.9k
+    // cycles end to end, and the polling warps compete with the working ones: 14.0 ms per fit (16 warps) against
+    // 11.0 ms for the wave kernels at config 2.  Kept selectable, off by default; same results either way.
+    p->dep_mode = false;
+    if (const char* e = getenv("SB2_DSGD_DEP")) p->dep_mode = atoi(e) != 0 && !p->with_yj && F4 <= 64;
+    auto choose_lanes = [&]() {
+        p->fast = F4 <= 64;
+        p->G = 32;
+        p->CH = 0;
+        if (p->dep_mode) {
+            p->CH = (F4 + 31) / 32;
+        } else if (p->fast) {
+            int g = 1;
+            while (g < 16 && 4 * g < F4) g <<= 1;
+            p->G = g;
+            p->CH = (F4 + g - 1) / g;
+            if (const char* e = getenv("SB2_DSGD_LANES")) {
+                const int ge = atoi(e);
+                if (ge > 0 && dsgd_shape_ok(ge, (F4 + ge - 1) / ge)) { p->G = ge; p->CH = (F4 + ge - 1) / ge; }
+            }
         }
-    }
-    const int threads = dsgd_threads(p->G);
-    p->W = threads / p->G;
-    if (const char* e = getenv("SB2_DSGD_GROUPS")) {
-        const int w = atoi(e);
-        if (w > 0 && w * p->G <= threads && (w * p->G) % 32 == 0) p->W = w;
-    }
+        const int threads = p->dep_mode ? 256 : dsgd_threads(p->G);
+        p->W = threads / p->G;
+        if (const char* e = getenv("SB2_DSGD_GROUPS")) {
+            const int w = atoi(e);
+            if (w > 0 && w * p->G <= dsgd_threads(p->G) && (w * p->G) % 32 == 0) p->W = w;
+        }
+    };
+    choose_lanes();
     // Blocks B (= CTAs = strata per sub-epoch) and cluster size C.  With thread-block clusters an item block hops
     // CTA -> CTA through distributed shared memory (~1k cycles) and only every C-th hop goes through L2
     // (~8k cycles), so small cells are affordable: B = K * C as large as the co-residency limit allows, but at
@@ -1143,11 +1240,11 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     const size_t budget = 200 * 1024;
     auto plan_smem = [&](int Bc, int Cc, bool* st_i, bool* st_u, size_t* used, int* ibuf) {
         const int mul = (int)ceil_div(nu_max, Bc), mil = (int)ceil_div(p->ni_max, Bc);
-        const size_t fixed = (size_t)(2 * (NW + 1) + 2 * P * Bc) * 4 + 64;
+        const size_t fixed = (size_t)(2 * (NW + 1) + 2 * P * Bc) * 4 + 64 + (p->dep_mode ? (size_t)(mul + mil) * 4 : 0);
         *ibuf = (int)round_up((int64_t)mil * (p->FP + 1), 4);
         const size_t need_i = (size_t)(Cc > 1 ? 2 : 1) * *ibuf * sizeof(float) + 16;
         const size_t need_u = (size_t)mul * (p->US + 3) * sizeof(float) + 16;
-        const size_t min_rec = 256 * 24;
+        const size_t min_rec = 256 * 32;
         *st_i = fixed + min_rec + need_i <= budget;
         *st_u = *st_i && fixed + min_rec + need_i + need_u <= budget;
         *used = fixed + (*st_i ? need_i : 0) + (*st_u ? need_u : 0);
@@ -1176,7 +1273,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         p->B = Bc; p->C = Cc;
         plan_smem(Bc, Cc, &p->stage_i, &p->stage_u, &smem_used, &p->ibuf);
         if (!p->stage_i) continue;
-        p->smem = smem_used + 256 * 24 + 64;
+        p->smem = smem_used + 256 * 32 + 64;
         dsgd_kernel_t kern = dsgd_kernel(p);
         int max_clusters = 0;
         cudaLaunchConfig_t cfg;
@@ -1226,6 +1323,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     PLAN_CUDA(cudaMallocAsync(&p->ul, n1 * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->il, n1 * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->r, n1 * 4, st));
+    if (p->dep_mode) PLAN_CUDA(cudaMallocAsync(&p->dep, n1 * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->off, (n_cells + 1) * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->wave_off, n_cells * (NW + 1) * 4, st));
     PLAN_CUDA(cudaMallocAsync(&p->flags, (size_t)B * 4, st));
@@ -1268,9 +1366,9 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     PREP_CUDA(cudaMallocAsync(&val2, n1 * 4, st));
     PREP_CUDA(cudaMallocAsync(&color_tmp, n1, st));
     PREP_CUDA(cudaMallocAsync(&cnt, (n_cells + 1) * 4, st));
-    PREP_CUDA(cudaMallocAsync(&status, 8, st));
+    PREP_CUDA(cudaMallocAsync(&status, 16, st));
     PREP_CUDA(cudaMemsetAsync(cnt, 0, (n_cells + 1) * 4, st));
-    PREP_CUDA(cudaMemsetAsync(status, 0, 8, st));
+    PREP_CUDA(cudaMemsetAsync(status, 0, 16, st));
     int end_bit = 1;
     while (((size_t)1 << end_bit) <= n_cells) ++end_bit;  // keys 0 .. n_cells (n_cells = "not mine / invalid")
     size_t tb1 = 0, tb2 = 0;
@@ -1278,7 +1376,7 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt, p->off, (int)(n_cells + 1), st);
     const size_t tb = std::max(tb1, tb2);
     PREP_CUDA(cudaMallocAsync(&tmp, tb + 16, st));
-    const size_t mask_bytes = (size_t)(max_ul + max_il) * 8;
+    const size_t mask_bytes = (size_t)(max_ul + max_il) * 12;  // 64-bit colour masks + int tail counters
     if (mask_bytes > 200 * 1024) {
         set_error("svd_plan: %d + %d rows per block exceed the colouring kernel's shared memory", max_ul, max_il);
         cleanup();
@@ -1300,12 +1398,12 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         PREP_CUDA(cudaFuncSetAttribute(dsgd_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_bytes));
         const unsigned grid = (unsigned)std::min<size_t>(n_cells, (size_t)sm_count() * 32);
         dsgd_color_kernel<<<grid, 32, mask_bytes, st>>>((int)n_cells, B, P, max_ul, max_il, p->off, val2, u, i, r,
-                                                        color_tmp, p->ul, p->il, p->r, p->wave_off, status);
+                                                        color_tmp, p->ul, p->il, p->r, p->wave_off, p->dep, status);
         launch_counter()++;
     }
-    int status_h[2] = {0, 0};
+    int status_h[4] = {0, 0, 0, 0};
     int n_loc = 0;
-    PREP_CUDA(cudaMemcpyAsync(status_h, status, 8, cudaMemcpyDeviceToHost, st));
+    PREP_CUDA(cudaMemcpyAsync(status_h, status, 16, cudaMemcpyDeviceToHost, st));
     PREP_CUDA(cudaMemcpyAsync(&n_loc, p->off + n_cells, 4, cudaMemcpyDeviceToHost, st));
     PREP_CUDA(cudaStreamSynchronize(st));
     PREP_CUDA(cudaGetLastError());
@@ -1315,6 +1413,11 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         return fail(SB2_ERR_INVALID);
     }
     p->n_loc = n_loc;
+    if (p->dep_mode && (!p->stage_u || !p->stage_i || status_h[2] >= 0xFFFF)) {
+        // rows not resident in shared memory, or a row with >= 65535 ratings in one cell: the wave kernels
+        p->dep_mode = false;
+        choose_lanes();
+    }
     if (p->with_yj) {
         // ur CSR of this rank's users, 1/sqrt|I_u|, item -> (local) raters CSR for the y_j application
         const int64_t nu = p->nu_loc;
@@ -1401,10 +1504,11 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
     // shared-memory plan: wave table + cell offsets, item buffer(s), user block, then as many of a cell's
     // records as still fit (the rest is read from global memory)
     int rec_cap = std::max(status_h[1], 1);
-    rec_cap = (int)std::min<size_t>((size_t)round_up(rec_cap, 4), (budget - smem_used) / 24 / 4 * 4);
+    const size_t rec_bytes = p->dep_mode ? 32 : 24;  // two buffers of (ul, il, r[, dep])
+    rec_cap = (int)std::min<size_t>((size_t)round_up(rec_cap, 4), (budget - smem_used) / rec_bytes / 4 * 4);
     p->rec_cap = rec_cap;
     p->max_cell = status_h[1];
-    p->smem = smem_used + (size_t)rec_cap * 24 + 64;
+    p->smem = smem_used + (size_t)rec_cap * rec_bytes + 64;
     *out = p;
     return SB2_OK;
 }
@@ -1448,6 +1552,8 @@ static int fill_args(sb2_svd_plan* p, DsgdArgs& a) {
     a.n_users = (int)p->nu_loc; a.n_items = (int)p->n_items; a.B = p->B; a.W = p->W;
     a.f = p->prm.n_factors; a.FP = p->FP; a.US = p->US;
     a.max_ul = (int)ceil_div(ceil_div(p->n_users, p->P), p->B); a.max_il = (int)ceil_div(p->ni_max, p->B);
+    a.dep = p->dep;
+    if (const char* e = getenv("SB2_DSGD_DEP_SYNC")) a.dep_sync = atoi(e);
     a.ul = p->ul; a.il = p->il; a.r = p->r; a.cell_off = p->off; a.wave_off = p->wave_off; a.rec_cap = p->rec_cap;
     a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags; a.status = p->status;
     a.isq = p->isq; a.cnt = p->cnt;
