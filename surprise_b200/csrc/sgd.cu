@@ -267,29 +267,64 @@ __device__ __forceinline__ void sgd_update(const DsgdArgs& a, float* prow, float
         if (NCH == 2) dot = part[0] + part[1];
         if (NCH == 3) dot = (part[0] + part[1]) + part[2];
         if (NCH == 4) dot = (part[0] + part[1]) + (part[2] + part[3]);
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
-        const float err = BIASED ? r - (a.mu + b_u + b_i + dot) : r - dot;
-        const float eg = err * isq;
         const float dp = 1.f - a.lr_pu * a.reg_pu, dq = 1.f - a.lr_qi * a.reg_qi, dy = 1.f - a.lr_yj * a.reg_yj;
+        // The decayed old values (1 - lr reg) p, (1 - lr reg) q do not depend on the error: they are computed in
+        // the shadow of the shuffle reduction (each stage is ~25 cycles during which this warp -- often the only
+        // active one on its scheduler -- would issue nothing), so that only one FMA per element remains on the
+        // critical path behind err.  Volatile asm keeps them between the shuffles where the source puts them.
+        float4 pd[NCH], qd[NCH];
+        auto scale4 = [](float4& o, float s, const float4& v) {
+            asm volatile("mul.rn.f32 %0, %4, %5;\n\tmul.rn.f32 %1, %4, %6;\n\tmul.rn.f32 %2, %4, %7;\n\tmul.rn.f32 %3, %4, %8;"
+                         : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "f"(s), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+        };
+        constexpr int NST = G >= 32 ? 5 : G >= 16 ? 4 : G >= 8 ? 3 : G >= 4 ? 2 : G >= 2 ? 1 : 0;  // shuffle stages
+        int done = 0;  // float4 scale operations issued so far (2 per chunk)
+        auto scale_some = [&](int upto) {
+#pragma unroll
+            for (int t = 0; t < 2 * NCH; ++t) {
+                if (t >= done && t < upto) {
+                    const int c = t >> 1;
+                    if (t & 1) scale4(qd[c], dq, q[c]);
+                    else {
+                        float4 po = p[c];
+                        if (PP) { po.x -= z[c].x; po.y -= z[c].y; po.z -= z[c].z; po.w -= z[c].w; }
+                        scale4(pd[c], dp, po);
+                    }
+                }
+            }
+            done = upto > done ? upto : done;
+        };
+        const float mub = BIASED ? (a.mu + b_u) + b_i : 0.f;
+        if (NST == 0) scale_some(2 * NCH);
+        {
+            int stage = 0;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const float other = __shfl_xor_sync(gmask, dot, o);
+                ++stage;
+                scale_some((2 * NCH * stage + NST - 1) / NST);
+                dot += other;
+            }
+        }
+        const float err = BIASED ? r - (mub + dot) : r - dot;
+        const float eg = err * isq;
         const float ep = a.lr_pu * err, eq = a.lr_qi * err, ey = a.lr_yj * err;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int ch = gl + c * G;
             const bool st = valid && ((c + 1 < NCH) || tail_ok);
             const float4 pz = p[c];  // p (+ z for SVD++)
-            float4 po = pz;
-            if (PP) { po.x -= z[c].x; po.y -= z[c].y; po.z -= z[c].z; po.w -= z[c].w; }
-            // p + lr (err q - reg p) = (1 - lr reg) p + (lr err) q: one multiply and one FMA per element
+            // p + lr (err q - reg p) = (1 - lr reg) p + (lr err) q: one multiply (above) and one FMA per element
             float4 pn, qn;
-            pn.x = fmaf(ep, q[c].x, dp * po.x);
-            pn.y = fmaf(ep, q[c].y, dp * po.y);
-            pn.z = fmaf(ep, q[c].z, dp * po.z);
-            pn.w = fmaf(ep, q[c].w, dp * po.w);
-            qn.x = fmaf(eq, pz.x, dq * q[c].x);
-            qn.y = fmaf(eq, pz.y, dq * q[c].y);
-            qn.z = fmaf(eq, pz.z, dq * q[c].z);
-            qn.w = fmaf(eq, pz.w, dq * q[c].w);
+            pn.x = fmaf(ep, q[c].x, pd[c].x);
+            pn.y = fmaf(ep, q[c].y, pd[c].y);
+            pn.z = fmaf(ep, q[c].z, pd[c].z);
+            pn.w = fmaf(ep, q[c].w, pd[c].w);
+            qn.x = fmaf(eq, pz.x, qd[c].x);
+            qn.y = fmaf(eq, pz.y, qd[c].y);
+            qn.z = fmaf(eq, pz.z, qd[c].z);
+            qn.w = fmaf(eq, pz.w, qd[c].w);
             if (st) {
                 row_st4<SU>(prow + 4 * ch, pn);
                 row_st4<SI>(qrow + 4 * ch, qn);

@@ -81,6 +81,10 @@ class Dataset(object):
                                  raw_uids=raw_u.tolist(), raw_iids=raw_i.tolist())
 
     def construct_testset(self, raw_testset):
+        if isinstance(raw_testset, tuple) and len(raw_testset) == 3 and isinstance(raw_testset[0], np.ndarray):
+            uids, iids, ratings = raw_testset     # array fast path: ratings still carry no offset
+            r = np.asarray(ratings, dtype=np.float64) + self.reader.offset
+            return list(zip(uids.tolist(), iids.tolist(), r.tolist()))
         return [(ruid, riid, r_ui_trans) for (ruid, riid, r_ui_trans, _) in raw_testset]
 
 
@@ -118,6 +122,16 @@ class DatasetAutoFolds(Dataset):
             self.raw_ratings = None
         else:
             raise ValueError("Must specify ratings file or dataframe.")
+
+    def n_raw_ratings(self):
+        return len(self._arrays[0]) if self._arrays is not None else len(self.raw_ratings)
+
+    def _take(self, idx):
+        """The raw ratings at positions idx: a list of the reference's raw tuples, or (array-backed dataset) the
+        three arrays sliced -- both are accepted by construct_trainset / construct_testset."""
+        if self._arrays is not None:
+            return tuple(a[idx] for a in self._arrays)
+        return [self.raw_ratings[k] for k in idx]
 
     def build_full_trainset(self):
         if self._arrays is not None:

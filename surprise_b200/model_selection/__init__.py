@@ -1,4 +1,5 @@
-from .split import KFold, PredefinedKFold, train_test_split
+from .split import KFold, PredefinedKFold, RepeatedKFold, ShuffleSplit, train_test_split
 from .validation import cross_validate, fit_and_score
 
-__all__ = ["KFold", "PredefinedKFold", "train_test_split", "cross_validate", "fit_and_score"]
+__all__ = ["KFold", "PredefinedKFold", "RepeatedKFold", "ShuffleSplit", "train_test_split", "cross_validate",
+           "fit_and_score"]

@@ -96,35 +96,32 @@ class AlgoBase(object):
         return cls._batch_estimate_of is not None and _func(cls.estimate) is _func(cls._batch_estimate_of)
 
     def test(self, testset, verbose=False):
+        """algo_base.py:191-218.  Device-backed algorithms get the whole testset in ONE estimate call: raw -> inner ids
+        through a table lookup (no per-pair exception handling), offset / clipping as array operations; only the
+        Prediction tuples the reference returns are built one by one."""
         rows = testset.tolist() if isinstance(testset, np.ndarray) else testset
         off = self.trainset.offset
         if not self._batched():
             return [self.predict(uid, iid, r - off, verbose=verbose) for (uid, iid, r) in rows]
         rows = list(rows)
         n = len(rows)
-        iu = np.full(n, -1, dtype=np.int32)
-        ii = np.full(n, -1, dtype=np.int32)
         ts = self.trainset
-        for k, (uid, iid, _) in enumerate(rows):
-            try:
-                iu[k] = ts.to_inner_uid(uid)
-            except ValueError:
-                pass
-            try:
-                ii[k] = ts.to_inner_iid(iid)
-            except ValueError:
-                pass
+        uids = [row[0] for row in rows]
+        iids = [row[1] for row in rows]
+        iu, ii = ts.to_inner_uids(uids), ts.to_inner_iids(iids)
         est, details = self._estimate_batch(iu, ii)
-        default = None
-        out = []
-        for k, (uid, iid, r) in enumerate(rows):
-            d = details[k]
-            e = est[k]
-            if d.get("was_impossible"):
-                if default is None:
-                    default = self.default_prediction()
-                e = default
-            out.append(self._finish(uid, iid, r - off, e, d, True, verbose))
+        est = np.asarray(est, dtype=np.float64).copy()
+        imp = np.fromiter((bool(d.get("was_impossible")) for d in details), dtype=bool, count=n)
+        if imp.any():
+            est[imp] = self.default_prediction()
+        est -= off
+        low, high = ts.rating_scale
+        est = np.maximum(low, np.minimum(high, est))      # est = min(high, est); est = max(low, est)
+        r_ui = (np.fromiter((row[2] for row in rows), dtype=np.float64, count=n) - off).tolist()
+        out = [Prediction(uid, iid, r, e, d) for uid, iid, r, e, d in zip(uids, iids, r_ui, est.tolist(), details)]
+        if verbose:
+            for pred in out:
+                print(pred)
         return out
 
     # -- shared fit-time helpers ----------------------------------------------------------------------

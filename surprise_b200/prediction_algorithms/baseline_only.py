@@ -24,6 +24,12 @@ class BaselineOnly(AlgoBase):
         self.bu, self.bi = self.compute_baselines()
         return self
 
+    def __setattr__(self, name, value):
+        # the reference's estimate() reads bu / bi live: assigning them after fit must drop the device copies
+        if name in ("bu", "bi", "trainset") and "_bias_dev" in self.__dict__:
+            self.__dict__["_bias_dev"] = None
+        object.__setattr__(self, name, value)
+
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_bias_dev"] = None

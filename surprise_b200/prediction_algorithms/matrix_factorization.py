@@ -58,6 +58,13 @@ class _FactorModel(AlgoBase):
                     else {"was_impossible": False}) for k in range(n)]
         return est, details
 
+    def __setattr__(self, name, value):
+        # the reference's estimate() reads pu / qi / bu / bi / yj live: assigning any of them after fit (warm starts,
+        # factor surgery) must not leave predict() / test() on stale device copies
+        if name in ("pu", "qi", "bu", "bi", "yj", "trainset"):
+            self.__dict__.pop("_dev_cache", None)
+        object.__setattr__(self, name, value)
+
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop("_dev_cache", None)
@@ -108,19 +115,49 @@ class SVD(_FactorModel):
         return self._params(trainset, biased=self.biased)
 
     def sgd(self, trainset):
-        pu, qi, _ = self._initial_factors(trainset)
+        """matrix_factorization.pyx:172-267.  The host draws the initial factors with numpy's RandomState (seed parity
+        with the reference; ~15 ms for 10^6 normals) while a helper thread uploads the ratings and stratifies them on
+        the device (sb2_svd_plan_create_dev); then reset -> epochs -> factors back as float64."""
+        import threading
         if self.verbose:
             for ep in range(self.n_epochs):
                 print("Processing epoch {}".format(ep))
-        d_u, d_i, d_r, n = self._coo_dev(trainset)
-        d_pu, d_qi = nat.to_dev(pu, np.float64), nat.to_dev(qi, np.float64)
-        d_bu = nat.empty_dev((trainset.n_users,), np.float64)
-        d_bi = nat.empty_dev((trainset.n_items,), np.float64)
         prm = self._sgd_params(trainset)
-        rc = nat.lib().sb2_svd_fit_dev(trainset.n_users, trainset.n_items, n, nat.ptr(d_u), nat.ptr(d_i), nat.ptr(d_r),
-                                       C.byref(prm), nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_bu), nat.ptr(d_bi),
-                                       nat.stream())
-        nat.check(rc)
+        lib = nat.lib()
+        torch = nat.torch_cuda()
+        stream, dev_index = nat.stream(), torch.cuda.current_device()
+        box = {}
+
+        def prepare():
+            try:
+                torch.cuda.set_device(dev_index)
+                d_u, d_i, d_r, n = self._coo_dev(trainset)
+                plan = C.c_void_p()
+                nat.check(lib.sb2_svd_plan_create_dev(trainset.n_users, trainset.n_items, n, nat.ptr(d_u), nat.ptr(d_i),
+                                                      nat.ptr(d_r), C.byref(prm), 0, None, None, stream, C.byref(plan)))
+                box["plan"] = plan
+            except BaseException as e:  # re-raised on the calling thread
+                box["error"] = e
+        helper = threading.Thread(target=prepare)
+        helper.start()
+        try:
+            pu, qi, _ = self._initial_factors(trainset)
+        finally:
+            helper.join()
+        if "error" in box:
+            raise box["error"]
+        plan = box["plan"]
+        try:
+            d_pu, d_qi = nat.to_dev(pu, np.float64), nat.to_dev(qi, np.float64)
+            d_bu = nat.empty_dev((trainset.n_users,), np.float64)
+            d_bi = nat.empty_dev((trainset.n_items,), np.float64)
+            nat.check(lib.sb2_svd_plan_reset_dev(plan, nat.ptr(d_pu), nat.ptr(d_qi), None, stream))
+            nat.check(lib.sb2_svd_plan_run(plan, int(self.n_epochs), stream))
+            nat.check(lib.sb2_svd_plan_read_dev(plan, nat.ptr(d_pu), nat.ptr(d_qi), nat.ptr(d_bu), nat.ptr(d_bi), None,
+                                                stream))
+            nat.check(lib.sb2_svd_plan_status(plan, stream))
+        finally:
+            lib.sb2_svd_plan_destroy(plan)
         self.pu, self.qi = d_pu.cpu().numpy(), d_qi.cpu().numpy()
         self.bu, self.bi = d_bu.cpu().numpy(), d_bi.cpu().numpy()
         self._dev_cache = None

@@ -137,6 +137,43 @@ class Trainset(object):
             self._raw2inner_id_items = ({k: k for k in range(self.n_items)} if ri is None
                                         else {raw: k for k, raw in enumerate(ri)})
 
+    def _inner_ids_of(self, raw, which):
+        """Vectorised raw -> inner id lookup for a whole testset: int32 array, -1 for ids the trainset does not
+        know (the reference's 'UKN__' ids, algo_base.py:140-147).  Integer raw ids of an array-backed trainset go
+        through a sorted table (np.searchsorted); anything else through the same dict the scalar lookups use."""
+        n = self.n_users if which == "u" else self.n_items
+        raws = getattr(self, "_raw_uids" if which == "u" else "_raw_iids", None)
+        have_dict = (self._raw2inner_id_users if which == "u" else self._raw2inner_id_items) is not None
+        arr = np.asarray(raw) if not isinstance(raw, np.ndarray) else raw
+        if arr.dtype.kind in "iu" and arr.ndim == 1:
+            if raws is None and not have_dict:       # Trainset.from_coo without raw ids: raw == inner
+                out = arr.astype(np.int64)
+                return np.where((out >= 0) & (out < n), out, -1).astype(np.int32)
+            if raws is not None:
+                tab = getattr(self, "_raw_table_" + which, None)
+                if tab is None:
+                    ra = np.asarray(raws)
+                    if ra.dtype.kind in "iu":
+                        order = np.argsort(ra, kind="stable")
+                        tab = (ra[order], order.astype(np.int32))
+                    else:
+                        tab = False
+                    setattr(self, "_raw_table_" + which, tab)
+                if tab is not False:
+                    keys, inner = tab
+                    pos = np.minimum(np.searchsorted(keys, arr), len(keys) - 1)
+                    return np.where(keys[pos] == arr, inner[pos], -1).astype(np.int32)
+        self._raw_maps()
+        d = self._raw2inner_id_users if which == "u" else self._raw2inner_id_items
+        seq = raw.tolist() if isinstance(raw, np.ndarray) else raw
+        return np.fromiter((d.get(x, -1) for x in seq), dtype=np.int32, count=len(seq))
+
+    def to_inner_uids(self, raw_uids):
+        return self._inner_ids_of(raw_uids, "u")
+
+    def to_inner_iids(self, raw_iids):
+        return self._inner_ids_of(raw_iids, "i")
+
     def to_inner_uid(self, ruid):
         self._raw_maps()
         try:

@@ -11,6 +11,7 @@ import surprise_b200 as sb
 from surprise_b200 import _native as nat
 from surprise_b200 import similarities as sims
 from surprise_b200 import synth
+from surprise_b200.trainset import Trainset
 from conftest import GOLDEN, ROOT
 
 
@@ -210,3 +211,84 @@ def test_trainset_ingest_fast_paths_match_reference_order():
     o = np.argsort(i, kind="stable")
     ptr, other, val = trainset._group_stable(i, u, rr, ts.n_items, np.bincount(i, minlength=ts.n_items))
     assert np.array_equal(other, u[o]) and np.array_equal(val, rr[o]) and ptr[-1] == len(rr)
+
+
+def test_row_stats_match_per_row_numpy():
+    """knns._row_stats stacks rows of equal length; every mean / sigma must carry the bits of np.mean / np.std applied
+    to that row alone (what knns.py:168-170 / :362-366 do), including rows longer than numpy's pairwise block (128)."""
+    from surprise_b200.prediction_algorithms.knns import _row_stats
+    rng = np.random.RandomState(3)
+    lens = np.concatenate((rng.randint(1, 12, 300), rng.randint(100, 400, 40), [1, 7, 8, 9, 127, 128, 129, 1000]))
+    n_x = len(lens)
+    x = np.repeat(np.arange(n_x, dtype=np.int32), lens)
+    n = len(x)
+    y = np.arange(n, dtype=np.int32) % 50
+    # every item id must be used: append one rating per missing id is not needed (50 ids all hit)
+    r = rng.randint(1, 11, n) * 0.5
+    ts = Trainset.from_coo(x, y, r, n_x, 50)
+    means, sigmas = _row_stats(ts, True, True)
+    ptr, _, val = ts.user_csr()
+    for k in range(n_x):
+        row = val[ptr[k]:ptr[k + 1]]
+        assert means[k] == np.mean(row) and sigmas[k] == np.std(row), k
+
+
+def test_shuffle_split_matches_reference_semantics():
+    """ShuffleSplit / train_test_split (reference split.py:506-536): trainset = head of the permutation, testset the
+    entries that follow; shuffle=False keeps file order (test = tail); sizes validated like the reference.  With
+    oracle/_ref present the split is also compared with the reference's own, seed for seed."""
+    import surprise_b200 as sb
+    from surprise_b200.model_selection import KFold, ShuffleSplit, train_test_split
+    n = 57
+    uids = np.arange(n) % 11
+    iids = (np.arange(n) * 7) % 13
+    rs = (np.arange(n) % 5 + 1).astype(np.float64)
+    data = sb.Dataset.load_from_arrays(uids, iids, rs, sb.Reader(rating_scale=(1, 5)))
+    tr, te = train_test_split(data, test_size=.25, random_state=7)
+    perm = np.random.RandomState(7).permutation(n)
+    n_test = int(np.ceil(.25 * n)); n_train = n - n_test
+    assert tr.n_ratings == n_train and len(te) == n_test
+    assert [(u, i) for (u, i, _) in te] == [(int(uids[k]), int(iids[k])) for k in perm[n_train:n_train + n_test]]
+    tr, te = train_test_split(data, test_size=10, shuffle=False)
+    assert [(u, i) for (u, i, _) in te] == [(int(uids[k]), int(iids[k])) for k in range(n - 10, n)]
+    tr, te = train_test_split(data, test_size=5, train_size=20, random_state=1)
+    assert tr.n_ratings == 20 and len(te) == 5
+    for bad in (dict(test_size=n), dict(train_size=n), dict(test_size=30, train_size=30), dict(test_size=-1)):
+        with pytest.raises(ValueError):
+            train_test_split(data, **bad)
+    folds = list(KFold(n_splits=4, random_state=3).split(data))
+    assert sum(len(te) for _, te in folds) == n and all(tr.n_ratings + len(te) == n for tr, te in folds)
+    assert len(list(ShuffleSplit(n_splits=3, test_size=.2, random_state=0).split(data))) == 3
+    # list-backed dataset: same rows as the array-backed one
+    rows = [(int(u), int(i), float(r), None) for u, i, r in zip(uids, iids, rs)]
+    data2 = sb.Dataset.load_from_arrays(uids, iids, rs, sb.Reader(rating_scale=(1, 5)))
+    data2._arrays, data2.raw_ratings = None, rows
+    tr2, te2 = train_test_split(data2, test_size=.25, random_state=7)
+    tr1, te1 = train_test_split(data, test_size=.25, random_state=7)
+    assert te1 == te2 and np.array_equal(tr1.coo()[2], tr2.coo()[2])
+    try:
+        import oracle
+        ref = oracle.import_reference()
+    except ImportError:
+        return
+    import pandas as pd
+    df = pd.DataFrame({"u": uids, "i": iids, "r": rs})
+    rdata = ref.Dataset.load_from_df(df, ref.Reader(rating_scale=(1, 5)))
+    from surprise.model_selection import train_test_split as ref_split
+    for kw in (dict(test_size=.25, random_state=7), dict(test_size=10, shuffle=False)):
+        rtr, rte = ref_split(rdata, **kw)
+        otr, ote = train_test_split(data, **kw)
+        assert [(int(u), int(i), float(r)) for u, i, r in rte] == [(int(u), int(i), float(r)) for u, i, r in ote]
+        assert rtr.n_ratings == otr.n_ratings and rtr.n_users == otr.n_users
+
+
+def test_vectorised_raw_to_inner_lookup():
+    ts = Trainset.from_coo(np.array([0, 1, 2, 0], dtype=np.int32), np.array([0, 0, 1, 2], dtype=np.int32),
+                           np.array([1., 2, 3, 4]), 3, 3, raw_uids=[10, 5, 77], raw_iids=["a", "b", "c"])
+    assert ts.to_inner_uids([5, 77, 10, 3]).tolist() == [1, 2, 0, -1]
+    assert ts.to_inner_iids(["c", "zz", "a"]).tolist() == [2, -1, 0]
+    assert ts.to_inner_uid(77) == 2
+    plain = Trainset.from_coo(np.array([0, 1, 2, 0], dtype=np.int32), np.array([0, 0, 1, 2], dtype=np.int32),
+                              np.array([1., 2, 3, 4]), 3, 3)
+    assert plain.to_inner_uids([0, 2, 3, -1]).tolist() == [0, 2, -1, -1]
+    assert plain.to_inner_iids(np.array([1, 5])).tolist() == [1, -1]
