@@ -583,16 +583,80 @@ static int sim_core(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
     return SB2_OK;
 }
 
+int sim_general_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
+                    int64_t nnz, int min_support, double global_mean, const double* x_biases, const double* y_biases,
+                    double shrinkage, int64_t row_begin, int64_t row_end, bool upper, double* sim_out, cudaStream_t st);
+
+__global__ void sim_visits_kernel(int64_t n_y, const int64_t* __restrict__ y_ptr, double* __restrict__ out) {
+    const int64_t y = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (y < n_y) {
+        const double len = (double)(y_ptr[y + 1] - y_ptr[y]);
+        v = len * len;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
+
+// Two implementations of the same four functions:
+//   digit   (sim_core above): dense masked contractions on the int8 tensor cores.  Cost ~ accumulators x n_x^2 x n_y,
+//           independent of the sparsity; exact for cosine / msd / pearson on grid ratings, 1e-9-class for
+//           pearson_baseline; needs non-negative ratings on a 1/d grid and unique (x, y) pairs.
+//   general (sim_general.cu): the reference's own loop nest on the CUDA cores, fp64, bit-identical to the reference for
+//           ANY input.  Cost ~ sum_y |yr[y]|^2 co-ratings (~1.8e10 / s on a B200 at n_x = 27k).
+// rating_denom == 0 (no grid / negative ratings) and duplicated pairs (detected by the pack kernel) always take the
+// general path: everything the reference accepts is computed, nothing is rejected.  Otherwise the cheaper one by the
+// cost model below runs; pearson_baseline prefers the general path unless the digit path is clearly (1.5x) faster,
+// because only the general path reproduces the reference's bits there.  SB2_SIM_PATH=digit|general overrides.
+static int sim_dispatch(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
+                        int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
+                        const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
+                        bool upper, cudaStream_t st) {
+    if (kind < 0 || kind > 3 || n_x <= 0 || n_y < 0 || row_begin < 0 || row_end > n_x || row_begin >= row_end) {
+        set_error("sim_build: invalid argument");
+        return SB2_ERR_INVALID;
+    }
+    bool use_digit = rating_denom > 0;
+    const char* force = getenv("SB2_SIM_PATH");
+    if (force && force[0] == 'g') use_digit = false;
+    if (use_digit && !(force && force[0] == 'd') && n_y > 0) {
+        DevBuf v_d;
+        SB2_TRY(v_d.alloc(sizeof(double), st));
+        SB2_CUDA(cudaMemsetAsync(v_d.p, 0, sizeof(double), st));
+        sim_visits_kernel<<<(unsigned)ceil_div(n_y, 256), 256, 0, st>>>(n_y, y_ptr, v_d.as<double>());
+        SB2_LAUNCH_CHECK();
+        double visits = 0.0;
+        SB2_CUDA(cudaMemcpyAsync(&visits, v_d.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SB2_CUDA(cudaStreamSynchronize(st));
+        const double rows = (double)(row_end - row_begin), frac = rows / (double)n_x;
+        // general: co-ratings of the shard's rows + zeroing / reading the 32-byte column records of every row
+        const double keep = upper ? 1.0 - ((double)row_begin + 0.5 * rows) / (double)n_x : 1.0;  // columns >= row_begin
+        const double t_general = frac * keep * visits / 1.5e10 + rows * (double)n_x * 64.0 / 3.0e12 + 2e-4;
+        // digit: accumulators x tiles x k at the measured 3.6 POP/s issued, + packing the dense panels
+        const int n_acc = kind == SB2_SIM_PEARSON_BASELINE ? 30 : kind == SB2_SIM_PEARSON ? 6 : 4;
+        const double n_pad = (double)round_up(n_x, 256), k_pad = (double)round_up(std::max<int64_t>(n_y, 1), 128);
+        const bool tri = (row_begin == 0 && row_end == n_x) || upper;
+        const double cols = tri ? (n_pad - (double)row_begin - 0.5 * rows) : n_pad;
+        const double t_digit = 2.0 * n_acc * rows * cols * k_pad / 3.6e15 + (n_acc / 2 + 3) * n_pad * k_pad / 4.0e12 + 3e-4;
+        const double bias = kind == SB2_SIM_PEARSON_BASELINE ? 1.5 : 1.0;
+        use_digit = t_digit * bias < t_general;
+    }
+    int rc = SB2_ERR_DUPLICATE;
+    if (use_digit)
+        rc = sim_core(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
+                      shrinkage, row_begin, row_end, sim_out, nullptr, upper, st);
+    if (rc != SB2_ERR_DUPLICATE) return rc;
+    return sim_general_dev(kind, n_x, n_y, y_ptr, x_idx, r, nnz, min_support, global_mean, x_biases, y_biases, shrinkage,
+                           row_begin, row_end, upper, sim_out, st);
+}
+
 int sim_build_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
                   int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
                   const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
                   cudaStream_t st) {
-    if (kind < 0 || kind > 3) {
-        set_error("sim_build: invalid argument");
-        return SB2_ERR_INVALID;
-    }
-    return sim_core(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
-                    shrinkage, row_begin, row_end, sim_out, nullptr, false, st);
+    return sim_dispatch(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
+                        shrinkage, row_begin, row_end, sim_out, false, st);
 }
 
 // row shard of a symmetric multi-rank build: only sim[i][j] with j >= row_begin is computed (tiles at or above the
@@ -602,12 +666,8 @@ int sim_build_upper_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr
                         int64_t nnz, int rating_denom, int min_support, double global_mean, const double* x_biases,
                         const double* y_biases, double shrinkage, int64_t row_begin, int64_t row_end, double* sim_out,
                         cudaStream_t st) {
-    if (kind < 0 || kind > 3) {
-        set_error("sim_build: invalid argument");
-        return SB2_ERR_INVALID;
-    }
-    return sim_core(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
-                    shrinkage, row_begin, row_end, sim_out, nullptr, true, st);
+    return sim_dispatch(kind, n_x, n_y, y_ptr, x_idx, r, nnz, rating_denom, min_support, global_mean, x_biases, y_biases,
+                        shrinkage, row_begin, row_end, sim_out, true, st);
 }
 
 // SlopeOne.fit (slope_one.pyx:44-80): u_ptr / i_idx / r is the ur CSR (items rated by each user)

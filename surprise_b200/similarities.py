@@ -64,10 +64,10 @@ def upload_inputs(kind, n_x, yr, x_biases=None, y_biases=None):
     # the checks that need a pass over the ratings run on the device copy (0.4 s of numpy at 20M ratings otherwise)
     if len(val) and (int(d_idx.min()) < 0 or int(d_idx.max()) >= n_x):
         raise IndexError("x index out of range for n_x=%d" % n_x)
+    # denom = 0: the ratings lie on none of the supported 1/d grids (or are negative): sb2_sim_build_dev then takes the
+    # general fp64 path (csrc/sim_general.cu: the reference's own summation order on the CUDA cores)
     denom = C.c_int(1)
     nat.check(nat.lib().sb2_rating_denominator_dev(nat.ptr(d_val), len(val), C.byref(denom), nat.stream()))
-    if denom.value == 0:
-        raise ValueError("similarity kernels need non-negative ratings on a 1/d grid, d in %s, with r*d <= 65535" % (_DENOMS,))
     inp = dict(n_x=n_x, n_y=n_y, nnz=len(val), denom=denom.value, ptr=nat.to_dev(ptr, np.int64), idx=d_idx, val=d_val,
                bx=None, by=None)
     if kind == "pearson_baseline":

@@ -195,7 +195,7 @@ def test_baselines_host_forms_bit_exact(u1, u1_golden):
 
 
 # ---- config 3 ---------------------------------------------------------------------------------------------
-def test_c3_full_shape_similarities_sampled_pairs():
+def test_c3_full_shape_similarities_sampled_pairs(monkeypatch):
     """27k x 138k, 20M half-star ratings, item-item: the whole pearson_baseline and cosine matrices are built on
     the device (5.8 GB each); 20 000 random entries are recomputed by the oracle from the two sparse rows."""
     import torch
@@ -214,21 +214,25 @@ def test_c3_full_shape_similarities_sampled_pairs():
     xptr = np.concatenate(([0], np.cumsum(np.bincount(i, minlength=n_x)))).astype(np.int64)
     d_pi, d_pj = torch.as_tensor(pi, device="cuda"), torch.as_tensor(pj, device="cuda")
     inp = sims.upload_inputs("pearson_baseline", n_x, yr, bi, bu)
-    for kind in ("pearson_baseline", "cosine"):
-        kw = dict(global_mean=mu, x_biases=bi, y_biases=bu, shrinkage=100) if kind == "pearson_baseline" else {}
-        sim = sims.build_device(kind, n_x, yr, 1, inputs=inp, **kw)
-        got = sim[d_pi, d_pj].cpu().numpy()
-        # symmetry and unit diagonal on a 4096-row band of the device matrix
-        band = sim[:4096, :4096]
-        assert bool(torch.equal(band, band.t())) and bool(torch.all(torch.diagonal(sim) == 1))
-        del sim, band
-        torch.cuda.empty_cache()
-        want = oracle.similarity_pairs(kind, pi, pj, xptr, u[o], r[o], 1, mu, bi, bu, 100.0)
-        want[pi == pj] = 1.0
-        if kind == "pearson_baseline":
-            assert np.allclose(got, want, rtol=0, atol=PB_ATOL), float(np.nanmax(np.abs(got - want)))
-        else:
-            assert np.array_equal(got, want)
+    want = {kind: oracle.similarity_pairs(kind, pi, pj, xptr, u[o], r[o], 1, mu, bi, bu, 100.0)
+            for kind in ("pearson_baseline", "cosine")}
+    for path in ("digit", "general"):     # int8 tensor-core contractions / the reference's loop nest in fp64
+        monkeypatch.setenv("SB2_SIM_PATH", path)
+        for kind in ("pearson_baseline", "cosine"):
+            kw = dict(global_mean=mu, x_biases=bi, y_biases=bu, shrinkage=100) if kind == "pearson_baseline" else {}
+            sim = sims.build_device(kind, n_x, yr, 1, inputs=inp, **kw)
+            got = sim[d_pi, d_pj].cpu().numpy()
+            # symmetry and unit diagonal on a 4096-row band of the device matrix
+            band = sim[:4096, :4096]
+            assert bool(torch.equal(band, band.t())) and bool(torch.all(torch.diagonal(sim) == 1))
+            del sim, band
+            torch.cuda.empty_cache()
+            w = want[kind].copy()
+            w[pi == pj] = 1.0
+            if kind == "pearson_baseline" and path == "digit":
+                assert np.allclose(got, w, rtol=0, atol=PB_ATOL), float(np.nanmax(np.abs(got - w)))
+            else:   # exact integer sums (cosine) / the reference's own fp64 arithmetic (general path): same bits
+                assert np.array_equal(got, w), (path, kind, float(np.nanmax(np.abs(got - w))))
 
 
 # ---- config 5 ---------------------------------------------------------------------------------------------

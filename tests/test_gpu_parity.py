@@ -28,6 +28,14 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+@pytest.fixture(params=("digit", "general"))
+def sim_path(request, monkeypatch):
+    """Both implementations of the similarity functions (csrc/sim.cu: int8 tensor-core contractions; csrc/sim_general.cu:
+    the reference's loop nest in fp64) must pass the same parity tests; without this the cost model would pick one."""
+    monkeypatch.setenv("SB2_SIM_PATH", request.param)
+    return request.param
+
+
 def test_device_is_blackwell():
     sm, maj, mnr, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
     nat.check(nat.lib().sb2_device_info(C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
@@ -55,7 +63,7 @@ def test_tcgen05_gemm_against_dp4a_and_numpy(shape):
 # ---- similarities -----------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", KINDS)
 @pytest.mark.parametrize("ms", (1, 4))
-def test_toy_similarities(toy, kind, ms):
+def test_toy_similarities(toy, kind, ms, sim_path):
     yr = (toy["y_ptr"], toy["x_idx"], toy["r"])
     if kind == "pearson_baseline":
         got = sims.pearson_baseline(8, yr, ms, float(toy["global_mean"]), toy["bx"], toy["by"])
@@ -67,7 +75,7 @@ def test_toy_similarities(toy, kind, ms):
     assert np.array_equal(got, got.T) and np.all(np.diag(got) == 1)
 
 
-def test_toy_dict_input_and_shuffle(toy):
+def test_toy_dict_input_and_shuffle(toy, sim_path):
     """The reference API takes a dict of lists; order inside a list must not matter."""
     import random
     yr = {0: [(0, 3), (1, 3), (2, 3), (5, 1), (6, 1.5), (7, 3)], 1: [(0, 4), (1, 4), (2, 4)],
@@ -86,7 +94,7 @@ def test_toy_dict_input_and_shuffle(toy):
 
 
 @pytest.mark.parametrize("orient", ("item", "user"))
-def test_u1_similarities_bit_exact(u1, u1_golden, u1_arrays, orient):
+def test_u1_similarities_bit_exact(u1, u1_golden, u1_arrays, orient, sim_path):
     ts, _ = u1
     ub = orient == "user"
     n_x = ts.n_users if ub else ts.n_items
@@ -107,7 +115,7 @@ def test_u1_similarities_bit_exact(u1, u1_golden, u1_arrays, orient):
     assert np.array_equal(got, got.T)
 
 
-def test_u1_row_shard_equals_full(u1):
+def test_u1_row_shard_equals_full(u1, sim_path):
     ts, _ = u1
     yr = ts.user_csr()
     full = sims.cosine(ts.n_items, yr, 1)
@@ -118,7 +126,7 @@ def test_u1_row_shard_equals_full(u1):
             assert np.array_equal(blk, full[b:e]), (kind, b, e)
 
 
-def test_float_ratings_similarities(floats):
+def test_float_ratings_similarities(floats, sim_path):
     """Jester-style two-decimal ratings run on the digit-split exact-integer path (denominator 100)."""
     ds = sb.Dataset.load_from_arrays(floats["uid"], floats["iid"], floats["rating"], sb.Reader(rating_scale=(-10, 10)))
     ts = ds.build_full_trainset()
@@ -137,7 +145,7 @@ def test_float_ratings_similarities(floats):
 
 
 @pytest.mark.parametrize("kind", KINDS)
-def test_sim_upper_shards_assemble_to_full(u1, kind):
+def test_sim_upper_shards_assemble_to_full(u1, kind, sim_path):
     """Symmetric multi-rank build emulated on one GPU: the upper-only shards of 3 ranks (sb2_sim_build_upper_dev),
     completed by the transposes the NCCL exchange would deliver, equal the single-GPU matrix bit for bit."""
     from surprise_b200 import distributed as D
@@ -176,6 +184,7 @@ def test_rating_denominator_on_device():
 
 @pytest.mark.parametrize("band_rows", (256, 512))
 def test_sim_banded_planes_bit_identical(u1, monkeypatch, band_rows):
+    monkeypatch.setenv("SB2_SIM_PATH", "digit")
     """The fp64 accumulator planes cover one band of row blocks at a time (bounded footprint); forcing 3 / 5 bands on
     the 1187-item fixture must not change one bit of any matrix: single-GPU symmetric build, plain row shard,
     upper-only shard, SlopeOne."""
@@ -207,15 +216,81 @@ def test_sim_banded_planes_bit_identical(u1, monkeypatch, band_rows):
 def test_similarity_errors():
     with pytest.raises(ZeroDivisionError):
         sims.msd(2, {0: [(0, 3.0)], 1: [(1, 4.0)]}, 0)
-    with pytest.raises(ValueError):
-        sims.cosine(2, {0: [(0, 3.0), (0, 4.0), (1, 2.0)]}, 1)   # duplicate (x, y)
-    with pytest.raises(ValueError):
-        sims.cosine(2, {0: [(0, np.pi), (1, 2.0)]}, 1)            # not on a 1/d grid
     empty = sims.cosine(3, {}, 1)
     assert np.array_equal(empty, np.eye(3))
 
 
-def test_synthetic_half_star_similarity_sampled():
+def _random_yr(rng, n_x, n_y, nnz, ratings, dup=0):
+    """yr CSR with unique (x, y) pairs (+ `dup` repeated pairs appended to random segments), list order shuffled."""
+    lin = rng.choice(n_x * n_y, nnz, replace=False)
+    y, x = lin // n_x, lin % n_x
+    if dup:
+        k = rng.choice(nnz, dup, replace=True)
+        y, x = np.concatenate((y, y[k])), np.concatenate((x, x[k]))
+    r = ratings(len(x))
+    o = rng.permutation(len(x))
+    y, x, r = y[o], x[o], r[o]
+    o = np.argsort(y, kind="stable")
+    y, x, r = y[o], x[o], r[o]
+    ptr = np.concatenate(([0], np.cumsum(np.bincount(y, minlength=n_y)))).astype(np.int64)
+    return ptr, x.astype(np.int32), r.astype(np.float64)
+
+
+@pytest.mark.parametrize("case", ("irrational", "negative", "duplicates", "duplicates_grid", "wide_range"))
+def test_general_similarity_path_bit_exact(case):
+    """Ratings the integer-digit panels cannot hold -- arbitrary doubles, negative values, 12 orders of magnitude of
+    dynamic range, duplicated (x, y) pairs (which the reference counts as separate co-ratings,
+    similarities.pyx:78-84) -- go through the general fp64 path in the reference's own summation order: every kind,
+    both min_support settings, EQUAL BIT FOR BIT to the oracle's restatement of the reference loops."""
+    rng = np.random.RandomState({"irrational": 1, "negative": 2, "duplicates": 3, "duplicates_grid": 4, "wide_range": 5}[case])
+    n_x, n_y = 150, 90
+    gen = {"irrational": lambda k: rng.uniform(0.5, 5.0, k) * np.pi / 3,
+           "negative": lambda k: rng.normal(0, 2.0, k),
+           "duplicates": lambda k: rng.uniform(1, 5, k),
+           "duplicates_grid": lambda k: rng.randint(1, 6, k).astype(np.float64),
+           "wide_range": lambda k: 10.0 ** rng.uniform(-6, 6, k)}[case]
+    ptr, idx, val = _random_yr(rng, n_x, n_y, 2500, gen, dup=120 if case.startswith("dup") else 0)
+    mu = float(np.mean(val))
+    bx, by = rng.normal(0, .3, n_x), rng.normal(0, .3, n_y)
+    yr = (ptr, idx, val)
+    for kind in KINDS:
+        for ms in (1, 3):
+            kw = (mu, bx, by, 50.0) if kind == "pearson_baseline" else ()
+            want = oracle.similarity(kind, n_x, ptr, idx, val, ms, *kw)
+            got = getattr(sims, kind)(n_x, yr, ms, *kw)
+            assert np.array_equal(got, want, equal_nan=True), (case, kind, ms, float(np.nanmax(np.abs(got - want))))
+    # a row shard equals the rows of the full build (the multi-rank similarity build on such ratings)
+    full = sims.build_device("pearson", n_x, yr, 1).cpu().numpy()
+    part = sims.build_device("pearson", n_x, yr, 1, row_begin=0, row_end=77).cpu().numpy()
+    assert np.array_equal(part, full[:77], equal_nan=True)
+    # dict input with a duplicated pair, as a user would pass it
+    d = {0: [(0, 3.0), (0, 4.0), (1, 2.0)], 1: [(1, np.pi), (0, 2.0)]}
+    p2, i2, v2 = oracle.flatten_yr(d, 2)
+    assert np.array_equal(sims.cosine(2, d, 1), oracle.similarity("cosine", 2, p2, i2, v2, 1))
+
+
+def test_general_path_forced_on_grid_ratings_matches_digit_path(u1, monkeypatch):
+    """SB2_SIM_PATH=general sends grid ratings through the general path too: on the reference's fixture both paths must
+    produce the same bits (cosine / msd / pearson: both exact; pearson_baseline: the general path IS the reference's
+    arithmetic, the digit path is within 1e-9 of it)."""
+    ts, _ = u1
+    yr = ts.user_csr()
+    mu = float(ts.global_mean)
+    bu, bi = oracle.baseline_als(ts.n_users, ts.n_items, *ts.user_csr(), *ts.item_csr(), mu)
+    monkeypatch.setenv("SB2_SIM_PATH", "digit")
+    digit = {k: getattr(sims, k)(ts.n_items, yr, 1, *((mu, bi, bu) if k == "pearson_baseline" else ())) for k in KINDS}
+    monkeypatch.setenv("SB2_SIM_PATH", "general")
+    for k in KINDS:
+        got = getattr(sims, k)(ts.n_items, yr, 1, *((mu, bi, bu) if k == "pearson_baseline" else ()))
+        if k == "pearson_baseline":
+            want = oracle.similarity(k, ts.n_items, *yr, 1, mu, bi, bu, 100.0)
+            assert np.array_equal(got, want)
+            assert np.allclose(got, digit[k], rtol=0, atol=PB_ATOL)
+        else:
+            assert np.array_equal(got, digit[k]), k
+
+
+def test_synthetic_half_star_similarity_sampled(sim_path):
     """ml-20M-style half-star ratings at a reduced shape: sampled entries against the oracle (bit-exact
     for the integer kinds), plus symmetry / diagonal / bounds on the whole matrix."""
     d = synth.ratings(3000, 1500, 200_000, step=0.5, seed=3)
@@ -768,7 +843,7 @@ def skewed():
     return d, ts
 
 
-def test_skewed_similarities_and_knn_bit_exact(skewed):
+def test_skewed_similarities_and_knn_bit_exact(skewed, sim_path):
     """Popular items / heavy users: long neighbour lists (beyond the per-lane buffers: refills) and large co-rating
     counts, item-based; every similarity kind against the oracle's full matrix, k-NN estimates bit for bit."""
     d, ts = skewed
