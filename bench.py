@@ -543,22 +543,40 @@ def secondary_metrics(nat, dist, rank, world):
         kw = dict(global_mean=float(ts.global_mean), x_biases=bi, y_biases=bu, shrinkage=100)
         inp = sims.upload_inputs("pearson_baseline", n_x, yr, bi, bu)     # ratings + baselines resident in HBM
         build = lambda kind, **k: D.sim_build_sharded(dist, kind, n_x, yr, 1, **k)
+        visits = float(np.sum(np.diff(yr[0]).astype(np.float64) ** 2))    # co-ratings: sum_y |yr[y]|^2
+        ops = 2.0 * 2.0 * n_x * n_x * n_y          # SURVEY 8d: 2 * G * n_x^2 * n_y with G = 2
+        out["c3_shape"] = "%d items x %d users, %d half-star ratings; output row-sharded on the devices" % (n_x, n_y, ts.n_ratings)
+        out["c3_algorithmic_int8_ops"] = ops
+        out["c3_co_ratings"] = visits
+        # default dispatch (cost model: here the general fp64 path for pearson_baseline, the tensor path for cosine)
+        os.environ.pop("SB2_SIM_PATH", None)
         out["c3_pearson_baseline_build_s_first_call"] = _timed_max(lambda: build("pearson_baseline", inputs=inp, **kw), dist, world, 1)
         out["c3_pearson_baseline_build_s"] = _timed_max(lambda: build("pearson_baseline", inputs=inp, **kw), dist, world, 3)
         out["c3_cosine_build_s"] = _timed_max(lambda: build("cosine", inputs=inp), dist, world, 3)
         out["c3_pearson_baseline_build_s_from_host_csr"] = _timed_max(lambda: build("pearson_baseline", **kw), dist, world, 2)
-        out["c3_shape"] = "%d items x %d users, %d half-star ratings; output row-sharded on the devices" % (n_x, n_y, ts.n_ratings)
-        ops = 2.0 * 2.0 * n_x * n_x * n_y          # SURVEY 8d: 2 * G * n_x^2 * n_y with G = 2
-        out["c3_algorithmic_int8_ops"] = ops
-        out["c3_pearson_baseline_algorithmic_TOPs"] = ops / out["c3_pearson_baseline_build_s"] / 1e12
-        # issued: 30 digit accumulators over the upper triangle = 15 full n_x^2 n_y contractions, against the G = 2 of
-        # the algorithmic count (why the 1e-9 contract needs all 6 + 6 digits of a_y, a_y^2)
-        out["c3_pearson_baseline_issued_TOPs"] = ops * 7.5 / out["c3_pearson_baseline_build_s"] / 1e12
-        out["c3_cosine_algorithmic_TOPs"] = ops / out["c3_cosine_build_s"] / 1e12
-        out["c3_frac_of_nominal_int8_4500_TOPs_per_gpu"] = {
-            "pearson_baseline_algorithmic": out["c3_pearson_baseline_algorithmic_TOPs"] / (4500.0 * world),
-            "pearson_baseline_issued": out["c3_pearson_baseline_issued_TOPs"] / (4500.0 * world),
-            "cosine_algorithmic": out["c3_cosine_algorithmic_TOPs"] / (4500.0 * world)}
+        # each implementation on its own: tensor = int8 tcgen05 contractions (csrc/sim.cu, 1e-9-class for
+        # pearson_baseline), general = the reference's loop nest in fp64 (csrc/sim_general.cu, bit-identical to it)
+        for path, tag in (("digit", "tensor_path"), ("general", "general_path")):
+            os.environ["SB2_SIM_PATH"] = path
+            build("pearson_baseline", inputs=inp, **kw)     # first use of this path grows the memory pool
+            out["c3_pearson_baseline_build_s_" + tag] = _timed_max(lambda: build("pearson_baseline", inputs=inp, **kw), dist, world, 3)
+            out["c3_cosine_build_s_" + tag] = _timed_max(lambda: build("cosine", inputs=inp), dist, world, 3)
+        os.environ.pop("SB2_SIM_PATH", None)
+        t_pb, t_cos = out["c3_pearson_baseline_build_s_tensor_path"], out["c3_cosine_build_s_tensor_path"]
+        # tensor path: issued = 30 digit accumulators over the upper triangle = 15 full n_x^2 n_y contractions, against
+        # the G = 2 of the algorithmic count (why the 1e-9 contract needs all 6 + 6 digits of a_y, a_y^2)
+        out["c3_tensor_path"] = {
+            "pearson_baseline_algorithmic_TOPs": ops / t_pb / 1e12, "pearson_baseline_issued_TOPs": ops * 7.5 / t_pb / 1e12,
+            "cosine_algorithmic_TOPs": ops / t_cos / 1e12,
+            "frac_of_nominal_int8_4500_TOPs_per_gpu": {"pearson_baseline_algorithmic": ops / t_pb / 1e12 / (4500.0 * world),
+                                                       "pearson_baseline_issued": ops * 7.5 / t_pb / 1e12 / (4500.0 * world),
+                                                       "cosine_algorithmic": ops / t_cos / 1e12 / (4500.0 * world)}}
+        # general path: per co-rating one 12-byte (x, r) entry read + one 32-byte column record read and written
+        t_g = out["c3_pearson_baseline_build_s_general_path"]
+        if world == 1:    # (symmetric shards skip the columns before their rows: the count below is the 1-GPU one)
+            out["c3_general_path"] = {"co_ratings_per_s": visits / t_g, "algorithmic_bytes_per_co_rating": 76,
+                                      "achieved_GBs": 76 * visits / t_g / 1e9,
+                                      "frac_of_measured_hbm": 76 * visits / t_g / 1e9 / peak}
         del inp, ts, yr, algo, d
         torch.cuda.empty_cache()
     except Exception as e:  # secondary numbers must never break the headline line

@@ -140,15 +140,247 @@ __device__ __forceinline__ void knn_fill(KnnBuf& q, const double* __restrict__ s
     }
 }
 
-__global__ void __launch_bounds__(KNN_WARPS * 32)
+// Short lists (len <= KNN_CAP, k <= KNN_KCAP -- the common case: |yr[y]| is ~10^2): threshold select.
+//   1. every lane loads its strided share of the neighbour similarities ONCE into shared memory as order-preserving
+//      integer keys (non-positive and NaN similarities can never contribute: key 0);
+//   2. the k-th largest key is found by bisection on the key VALUE: count(key >= mid) with one redux.sync.add per
+//      step, starting from the [min, max] of the candidates and stopping as soon as a cut with exactly k candidates
+//      above it is found -- typically ~10-15 steps, against k rounds of three reductions each;
+//   3. the <= k survivors are ranked among themselves in the total order (sim desc, position asc) -- exactly the
+//      order heapq.nlargest returns them in -- and the weighted sums are accumulated in that order in round-to-nearest
+//      fp64, every lane identically: same operations in the same sequence as the reference, same bits.
+constexpr int KNN_CAP = 512;    // candidates per warp held in shared memory
+constexpr int KNN_SLOTS = KNN_CAP / 32;
+constexpr int KNN_KCAP = 128;   // survivors per warp
+constexpr unsigned long long KNN_KEY0 = 0x8000000000000000ull;  // knn_key(0.0)
+
+struct KnnSums {
+    double sum_sim, sum_r;
+    int ak;
+};
+
+template <class TermFn>
+__device__ __forceinline__ KnnSums knn_select_short(const double* __restrict__ srow, const int32_t* __restrict__ idx, int len,
+                                                    int k, int lane, unsigned long long* __restrict__ ckey /* [KNN_CAP] */,
+                                                    unsigned long long* __restrict__ skey /* [KNN_KCAP] */,
+                                                    int* __restrict__ spos /* [2 * KNN_KCAP] */, TermFn term_of) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int n_slots = (len + 31) >> 5;   // candidate a = lane + 32 * slot, keys at ckey[slot * 32 + lane]
+    // 1. keys of this lane's candidates
+    int n_pos = 0;
+    unsigned long long kmax = 0ull, kmin = ~0ull;
+    for (int slot = 0; slot < n_slots; ++slot) {
+        const int a = lane + 32 * slot;
+        unsigned long long key = 0ull;
+        if (a < len) {
+            key = knn_key(srow[idx[a]]);
+            if (key <= KNN_KEY0) key = 0ull;   // sim <= 0 (or NaN): never part of the sums (knns.py:110-113)
+        }
+        ckey[slot * 32 + lane] = key;
+        if (key) { ++n_pos; kmax = key > kmax ? key : kmax; kmin = key < kmin ? key : kmin; }
+    }
+    n_pos = __reduce_add_sync(FULL, n_pos);
+    KnnSums out{0.0, 0.0, 0};
+    if (n_pos == 0) return out;
+    const int kk = n_pos < k ? n_pos : k;
+    // 2. cut: the largest T with count(key >= T) >= kk; stop early on a cut with exactly kk candidates above it
+    unsigned long long cut = 1ull;   // n_pos <= k: every positive candidate survives
+    int n_ge = n_pos;
+    if (n_pos > kk) {
+        // warp-wide max / min of the 64-bit keys (two 32-bit reductions each)
+        unsigned h = (unsigned)(kmax >> 32);
+        const unsigned mhi = __reduce_max_sync(FULL, h);
+        const unsigned mlo = __reduce_max_sync(FULL, h == mhi ? (unsigned)kmax : 0u);
+        h = (unsigned)(kmin >> 32);
+        const unsigned nhi = __reduce_min_sync(FULL, h);
+        const unsigned nlo = __reduce_min_sync(FULL, h == nhi ? (unsigned)kmin : 0xFFFFFFFFu);
+        unsigned long long lo = ((unsigned long long)nhi << 32) | nlo;     // count(>= lo) = n_pos >= kk
+        unsigned long long hi = ((unsigned long long)mhi << 32) | mlo;     // count(>= hi + 1) = 0 < kk
+        cut = lo;
+        // Bisection on the key VALUE with both ends snapped to candidate values after every step (lo: the smallest
+        // candidate >= mid, hi: the largest candidate < mid), so the number of steps is bounded by the number of
+        // DISTINCT similarities in the range (msd / pearson on star ratings produce many equal ones) as well as by
+        // the 64 bits of the key.  Invariants: lo and hi are candidate keys, count(>= lo) >= kk, count(> hi) < kk.
+        auto warp_min64 = [&](unsigned long long v) {
+            const unsigned a = __reduce_min_sync(FULL, (unsigned)(v >> 32));
+            const unsigned b2 = __reduce_min_sync(FULL, (unsigned)(v >> 32) == a ? (unsigned)v : 0xFFFFFFFFu);
+            return ((unsigned long long)a << 32) | b2;
+        };
+        auto warp_max64 = [&](unsigned long long v) {
+            const unsigned a = __reduce_max_sync(FULL, (unsigned)(v >> 32));
+            const unsigned b2 = __reduce_max_sync(FULL, (unsigned)(v >> 32) == a ? (unsigned)v : 0u);
+            return ((unsigned long long)a << 32) | b2;
+        };
+        while (lo < hi) {
+            const unsigned long long mid = lo + ((hi - lo) >> 1) + 1;       // lo < mid <= hi
+            int c = 0;
+            unsigned long long up = ~0ull, down = 0ull;   // smallest key >= mid, largest key < mid
+            for (int slot = 0; slot < n_slots; ++slot) {
+                const unsigned long long key = ckey[slot * 32 + lane];
+                const bool ge = key >= mid;
+                c += ge;
+                up = (ge && key < up) ? key : up;
+                down = (!ge && key > down) ? key : down;
+            }
+            c = __reduce_add_sync(FULL, c);
+            if (c >= kk) {
+                lo = warp_min64(up); cut = lo; n_ge = c;   // count(>= lo) is still c
+                if (c == kk) break;
+            } else {
+                hi = warp_max64(down);                      // >= lo: count(>= lo) >= kk > c
+            }
+        }
+        if (lo >= hi) cut = lo;
+    }
+    // 3. survivors: key > cut all; key == cut in position order until kk are there (heapq.nlargest keeps list order
+    //    among equal keys), i.e. the n_ge - kk LAST candidates equal to `cut` are left out
+    int n_eq_keep = 0x7FFFFFFF;
+    if (n_ge > kk) {
+        int c_gt = 0;
+        for (int slot = 0; slot < n_slots; ++slot) c_gt += ckey[slot * 32 + lane] > cut;
+        n_eq_keep = kk - __reduce_add_sync(FULL, c_gt);
+    }
+    // compaction in position order (slot-major, lane-minor = ascending position)
+    int base = 0, eq_seen = 0;
+    for (int slot = 0; slot < n_slots; ++slot) {
+        const unsigned long long key = ckey[slot * 32 + lane];
+        const bool eq = key == cut, gt = key > cut;
+        const unsigned below = (1u << lane) - 1u;
+        const unsigned m_eq = __ballot_sync(FULL, eq);
+        const bool take = gt || (eq && eq_seen + __popc(m_eq & below) < n_eq_keep);
+        const unsigned m = __ballot_sync(FULL, take);
+        if (take) {
+            const int o = base + __popc(m & below);
+            skey[o] = key;
+            spos[o] = lane + 32 * slot;
+        }
+        base += __popc(m);
+        eq_seen += __popc(m_eq);
+    }
+    __syncwarp(FULL);
+    // rank of every survivor in (key desc, pos asc) -- survivors are in ascending position, so among equal keys the
+    // earlier index wins -- and scatter into sorted order: keys into the (now free) head of ckey, positions into the
+    // second half of spos.  The ranks are a permutation of 0 .. kk-1: no two lanes write the same slot.
+    for (int j0 = 0; j0 < kk; j0 += 64) {   // lane handles survivors j0 + lane and j0 + 32 + lane in one sweep
+        const int ja = j0 + lane, jb = j0 + 32 + lane;
+        const unsigned long long ka = ja < kk ? skey[ja] : 0ull, kb = jb < kk ? skey[jb] : 0ull;
+        int ra = 0, rb = 0;
+        for (int t = 0; t < kk; ++t) {
+            const unsigned long long kt = skey[t];
+            ra += (kt > ka) || (kt == ka && t < ja);
+            rb += (kt > kb) || (kt == kb && t < jb);
+        }
+        if (ja < kk) { ckey[ra] = ka; spos[KNN_KCAP + ra] = spos[ja]; }
+        if (jb < kk) { ckey[rb] = kb; spos[KNN_KCAP + rb] = spos[jb]; }
+    }
+    __syncwarp(FULL);
+    // ordered sums: one neighbour per lane computes its term, then every lane folds the batch in order
+    for (int j0 = 0; j0 < kk; j0 += 32) {
+        const int j = j0 + lane;
+        double bs = 0.0, term = 0.0;
+        if (j < kk) {
+            bs = knn_unkey(ckey[j]);
+            term = term_of(bs, spos[KNN_KCAP + j]);
+        }
+        const int nb = kk - j0 < 32 ? kk - j0 : 32;
+        for (int t = 0; t < nb; ++t) {
+            out.sum_sim = __dadd_rn(out.sum_sim, __shfl_sync(FULL, bs, t));
+            out.sum_r = __dadd_rn(out.sum_r, __shfl_sync(FULL, term, t));
+        }
+    }
+    out.ak = kk;
+    __syncwarp(FULL);   // the buffers are reused by this warp's next pair
+    return out;
+}
+
+// Long lists (len > KNN_CAP) or very large k: lane-local sorted buffers + one selection round per neighbour (see the
+// header comment of this section).  Kept out of line: its register needs must not cap the short path's occupancy.
+template <class TermFn>
+__device__ __noinline__ KnnSums knn_select_long(const double* __restrict__ srow, const int32_t* __restrict__ idx, int64_t len,
+                                    int k, int lane, unsigned long long* __restrict__ bkey /* [KNN_L][32] */,
+                                    int* __restrict__ bpos /* [KNN_L][32] */, TermFn term_of) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    double sum_sim = 0.0, sum_r = 0.0;
+    int ak = 0;
+    KnnBuf q;
+    knn_fill(q, srow, idx, len, lane, false, 0ull, 0);
+    // the sorted lane buffers live in shared memory ([slot][lane]: conflict-free) so that the head is one
+    // indexed read per round instead of a select chain over registers (the kernel is issue-bound)
+#pragma unroll
+    for (int u = 0; u < KNN_L; ++u) { bkey[u * 32 + lane] = q.key[u]; bpos[u * 32 + lane] = q.pos[u]; }
+    int head = 0;
+    const int64_t rounds = len < (int64_t)k ? len : (int64_t)k;
+    // Selection runs in batches of 32 rounds that touch only registers; lane j keeps the j-th winner of the
+    // batch.  The ratings (and neighbour baselines) of a batch are then gathered by all lanes at once and the
+    // two sums advance in selection order from lane 0 upwards -- one memory round trip per batch instead
+    // of one per neighbour in the dependent chain.
+    bool done = false;
+    for (int64_t t0 = 0; t0 < rounds && !done; t0 += 32) {
+        const int batch = (int)((rounds - t0) < 32 ? (rounds - t0) : 32);
+        int nb = 0;
+        double my_bs = 0.0;
+        int my_bp = 0;
+        for (int t = 0; t < batch; ++t) {
+            // refill lanes that ran dry but had dropped candidates (the bound is the last entry they gave out)
+            const bool dry = head == q.cnt && q.dropped;
+            if (__any_sync(FULL, dry)) {
+                if (dry) {
+                    const unsigned long long bk = bkey[(KNN_L - 1) * 32 + lane];
+                    const int bp = bpos[(KNN_L - 1) * 32 + lane];
+                    knn_fill(q, srow, idx, len, lane, true, bk, bp);
+#pragma unroll
+                    for (int u = 0; u < KNN_L; ++u) { bkey[u * 32 + lane] = q.key[u]; bpos[u * 32 + lane] = q.pos[u]; }
+                    head = 0;
+                }
+                __syncwarp(FULL);
+            }
+            // head of this lane's buffer (entries are kept best-first)
+            unsigned long long hk = 0ull;
+            int hp = 0x7FFFFFFF;
+            if (head < q.cnt) { hk = bkey[head * 32 + lane]; hp = bpos[head * 32 + lane]; }
+            const unsigned hi = (unsigned)(hk >> 32);
+            const unsigned m_hi = __reduce_max_sync(FULL, hi);
+            bool alive = hi == m_hi && hk != 0ull;
+            const unsigned lo = alive ? (unsigned)hk : 0u;
+            const unsigned m_lo = __reduce_max_sync(FULL, lo);
+            alive = alive && lo == m_lo;
+            const unsigned long long bk = ((unsigned long long)m_hi << 32) | m_lo;
+            if (bk == 0ull) { done = true; break; }  // nothing (or only NaNs) left
+            const int bp = __reduce_min_sync(FULL, alive ? hp : 0x7FFFFFFF);
+            const double bs = knn_unkey(bk);
+            if (!(bs > 0.0)) { done = true; break; }  // everything that follows is <= 0 and contributes nothing
+            if (alive && hp == bp) ++head;
+            if (lane == nb) { my_bs = bs; my_bp = bp; }
+            ++nb;
+        }
+        const double term = lane < nb ? term_of(my_bs, my_bp) : 0.0;
+        for (int j = 0; j < nb; ++j) {
+            sum_sim = __dadd_rn(sum_sim, __shfl_sync(FULL, my_bs, j));
+            sum_r = __dadd_rn(sum_r, __shfl_sync(FULL, term, j));
+        }
+        ak += nb;
+    }
+    __syncwarp(FULL);
+    return KnnSums{sum_sim, sum_r, ak};
+}
+
+#ifndef SB2_KNN_MIN_BLOCKS
+#define SB2_KNN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(KNN_WARPS * 32, SB2_KNN_MIN_BLOCKS)
 knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t* __restrict__ y, int64_t n_x,
                    const double* __restrict__ sim, int64_t sim_ld, const int64_t* __restrict__ y_ptr,
                    const int32_t* __restrict__ x_idx, const double* __restrict__ r, int k, int min_k, int mode,
                    double mu, const double* __restrict__ bx, const double* __restrict__ by, double* __restrict__ est,
                    int32_t* __restrict__ actual_k, uint8_t* __restrict__ impossible) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    __shared__ unsigned long long bkey_s[KNN_WARPS][KNN_L][32];
-    __shared__ int bpos_s[KNN_WARPS][KNN_L][32];
+    // long-list path: sorted lane buffers [KNN_L][32] of keys / positions.  Short-list path: candidate keys
+    // [KNN_SLOTS][32] (their head is reused for the sorted survivor keys), survivor keys, survivor positions
+    // (first half: in position order, second half: sorted)
+    __shared__ unsigned long long bkey_s[KNN_WARPS][KNN_CAP];
+    __shared__ int bpos_s[KNN_WARPS][KNN_L * 32 > 2 * KNN_KCAP ? KNN_L * 32 : 2 * KNN_KCAP];
+    __shared__ unsigned long long skey_s[KNN_WARPS][KNN_KCAP];
+    static_assert(KNN_KCAP <= KNN_CAP && KNN_L * 32 <= KNN_CAP, "buffer reuse");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int64_t p = blockIdx.x * (int64_t)KNN_WARPS + w; p < n_pairs; p += (int64_t)gridDim.x * KNN_WARPS) {
         const int32_t xx = x[p], yy = y[p];
@@ -169,80 +401,24 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
             const int64_t b = y_ptr[yy], len = y_ptr[yy + 1] - b;
             const double* srow = sim + (size_t)xx * (size_t)sim_ld;
             const int32_t* idx = x_idx + b;
-            KnnBuf q;
-            knn_fill(q, srow, idx, len, lane, false, 0ull, 0);
-            // the sorted lane buffers live in shared memory ([slot][lane]: conflict-free) so that the head is one
-            // indexed read per round instead of a select chain over registers (the kernel is issue-bound)
-#pragma unroll
-            for (int u = 0; u < KNN_L; ++u) { bkey_s[w][u][lane] = q.key[u]; bpos_s[w][u][lane] = q.pos[u]; }
-            int head = 0;
+            // per-neighbour term of the weighted sum (knns.py:113 / :195 / :296-297 / :389)
+            auto term_of = [&](double bs, int pos) -> double {
+                const double rr = r[b + pos];
+                if (mode == 0) return __dmul_rn(bs, rr);
+                const int32_t nbr = idx[pos];
+                if (mode == 3) return __dmul_rn(bs, __dsub_rn(rr, bx[nbr]));
+                if (mode == 4) return __ddiv_rn(__dmul_rn(bs, __dsub_rn(rr, bx[nbr])), by[nbr]);
+                const double nb_bsl = __dadd_rn(__dadd_rn(mu, bx[nbr]), by[yy]);
+                return __dmul_rn(bs, __dsub_rn(rr, nb_bsl));
+            };
             double sum_sim = 0.0, sum_r = 0.0;
             ak = 0;
-            const int64_t rounds = len < (int64_t)k ? len : (int64_t)k;
-            // Selection runs in batches of 32 rounds that touch only registers; lane j keeps the j-th winner of the
-            // batch.  The ratings (and neighbour baselines) of a batch are then gathered by all lanes at once and the
-            // two sums advance in selection order from lane 0 upwards -- one memory round trip per batch instead
-            // of one per neighbour in the dependent chain.
-            bool done = false;
-            for (int64_t t0 = 0; t0 < rounds && !done; t0 += 32) {
-                const int batch = (int)((rounds - t0) < 32 ? (rounds - t0) : 32);
-                int nb = 0;
-                double my_bs = 0.0;
-                int my_bp = 0;
-                for (int t = 0; t < batch; ++t) {
-                    // refill lanes that ran dry but had dropped candidates (the bound is the last entry they gave out)
-                    const bool dry = head == q.cnt && q.dropped;
-                    if (__any_sync(FULL, dry)) {
-                        if (dry) {
-                            const unsigned long long bk = bkey_s[w][KNN_L - 1][lane];
-                            const int bp = bpos_s[w][KNN_L - 1][lane];
-                            knn_fill(q, srow, idx, len, lane, true, bk, bp);
-#pragma unroll
-                            for (int u = 0; u < KNN_L; ++u) { bkey_s[w][u][lane] = q.key[u]; bpos_s[w][u][lane] = q.pos[u]; }
-                            head = 0;
-                        }
-                        __syncwarp(FULL);
-                    }
-                    // head of this lane's buffer (entries are kept best-first)
-                    unsigned long long hk = 0ull;
-                    int hp = 0x7FFFFFFF;
-                    if (head < q.cnt) { hk = bkey_s[w][head][lane]; hp = bpos_s[w][head][lane]; }
-                    const unsigned hi = (unsigned)(hk >> 32);
-                    const unsigned m_hi = __reduce_max_sync(FULL, hi);
-                    bool alive = hi == m_hi && hk != 0ull;
-                    const unsigned lo = alive ? (unsigned)hk : 0u;
-                    const unsigned m_lo = __reduce_max_sync(FULL, lo);
-                    alive = alive && lo == m_lo;
-                    const unsigned long long bk = ((unsigned long long)m_hi << 32) | m_lo;
-                    if (bk == 0ull) { done = true; break; }  // nothing (or only NaNs) left
-                    const int bp = __reduce_min_sync(FULL, alive ? hp : 0x7FFFFFFF);
-                    const double bs = knn_unkey(bk);
-                    if (!(bs > 0.0)) { done = true; break; }  // everything that follows is <= 0 and contributes nothing
-                    if (alive && hp == bp) ++head;
-                    if (lane == nb) { my_bs = bs; my_bp = bp; }
-                    ++nb;
-                }
-                // per-neighbour term of the weighted sum, one neighbour per lane
-                double term = 0.0;
-                if (lane < nb) {
-                    const double rr = r[b + my_bp];
-                    if (mode == 0) {
-                        term = __dmul_rn(my_bs, rr);
-                    } else if (mode == 3) {
-                        term = __dmul_rn(my_bs, __dsub_rn(rr, bx[idx[my_bp]]));
-                    } else if (mode == 4) {
-                        const int32_t nbr = idx[my_bp];
-                        term = __ddiv_rn(__dmul_rn(my_bs, __dsub_rn(rr, bx[nbr])), by[nbr]);
-                    } else {
-                        const double nb_bsl = __dadd_rn(__dadd_rn(mu, bx[idx[my_bp]]), by[yy]);
-                        term = __dmul_rn(my_bs, __dsub_rn(rr, nb_bsl));
-                    }
-                }
-                for (int j = 0; j < nb; ++j) {
-                    sum_sim = __dadd_rn(sum_sim, __shfl_sync(FULL, my_bs, j));
-                    sum_r = __dadd_rn(sum_r, __shfl_sync(FULL, term, j));
-                }
-                ak += nb;
+            if (len <= KNN_CAP && k <= KNN_KCAP) {
+                const KnnSums o = knn_select_short(srow, idx, (int)len, k, lane, bkey_s[w], skey_s[w], bpos_s[w], term_of);
+                sum_sim = o.sum_sim; sum_r = o.sum_r; ak = o.ak;
+            } else {
+                const KnnSums o = knn_select_long(srow, idx, len, k, lane, bkey_s[w], bpos_s[w], term_of);
+                sum_sim = o.sum_sim; sum_r = o.sum_r; ak = o.ak;
             }
             if (mode != 0) {
                 if (ak < min_k) sum_r = 0.0;
