@@ -374,31 +374,22 @@ def knn_predict_sharded(dist, block, row_begin, row_end, n_x, x, y, yr, k, min_k
 # accumulator sums of a contiguous range of users and a contiguous range of items (sb2_nmf_plan_epoch_dev) and
 # the new factor rows are all-gathered after every epoch (NCCL; pu is 58 MB at Netflix scale).
 # ------------------------------------------------------------------------------------------------------------
-def even_ranges(n, world):
-    """world contiguous ranges covering [0, n) with sizes differing by at most one."""
-    return [((n * r) // world, (n * (r + 1)) // world) for r in range(world)]
-
-
-def _all_gather_rows(dist, full, ranges, rank):
-    """In-place: every rank contributes rows ranges[rank] of `full` (2-D CUDA tensor) and receives all others."""
-    import torch
-    world = len(ranges)
-    rows_max = max(hi - lo for lo, hi in ranges)
-    lo, hi = ranges[rank]
-    pad = torch.zeros((rows_max, full.shape[1]), dtype=full.dtype, device=full.device)
-    pad[:hi - lo] = full[lo:hi]
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
-    for r, (a, b) in enumerate(ranges):
-        if r != rank:
-            full[a:b] = parts[r][:b - a]
+def block_ranges(n, world):
+    """world contiguous ranges of ceil(n / world) rows each (the last ones shorter or empty): equal-sized blocks are
+    what an in-place NCCL all-gather needs."""
+    per = (n + world - 1) // world
+    return per, [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
 
 
 def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0, stats=None):
     """u, i, r: all_ratings COO (host arrays, identical on every rank); prm: _native.NmfParams; pu0 / qi0: the
     rng.uniform initial factors.  Returns (pu, qi, bu, bi) as float64 numpy arrays, identical on every rank and
     bit-identical to the single-GPU fit.  stats (dict, optional) receives 'epochs_s': the wall clock of the epoch
-    loop alone (device-synchronised, barrier on both sides), without upload / plan creation / download."""
+    loop alone (device-synchronised, barrier on both sides), without upload / plan creation / download.
+
+    Rank g evaluates the ordered accumulator sums of user block g and item block g (equal-sized contiguous blocks);
+    after every epoch the new rows are all-gathered IN PLACE (the factor buffers are padded to world x block rows and
+    each rank's block is the slice NCCL expects, so no staging copies: one all_gather_into_tensor per matrix)."""
     import ctypes as C
     import time
     from . import _native as nat
@@ -406,16 +397,23 @@ def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0, stats=None):
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
     lib = nat.lib()
+    f = prm.n_factors
     d_u, d_i, d_r = nat.to_dev(u, np.int32), nat.to_dev(i, np.int32), nat.to_dev(r, np.float64)
-    pu = [nat.to_dev(pu0, np.float64), None]
-    qi = [nat.to_dev(qi0, np.float64), None]
-    pu[1], qi[1] = torch.empty_like(pu[0]), torch.empty_like(qi[0])
-    bu = torch.zeros(n_users, dtype=torch.float64, device=pu[0].device)
-    bi = torch.zeros(n_items, dtype=torch.float64, device=pu[0].device)
+    per_u, ur = block_ranges(n_users, world)
+    per_i, ir = block_ranges(n_items, world)
+    dev = nat.device()
+
+    def padded(a0, per):
+        t = torch.zeros((per * world, f), dtype=torch.float64, device=dev)
+        t[:a0.shape[0]] = nat.to_dev(a0, np.float64)
+        return t
+    pu = [padded(pu0, per_u), torch.zeros((per_u * world, f), dtype=torch.float64, device=dev)]
+    qi = [padded(qi0, per_i), torch.zeros((per_i * world, f), dtype=torch.float64, device=dev)]
+    bu = torch.zeros(n_users, dtype=torch.float64, device=dev)
+    bi = torch.zeros(n_items, dtype=torch.float64, device=dev)
     plan = C.c_void_p()
     nat.check(lib.sb2_nmf_plan_create_dev(n_users, n_items, len(r), nat.ptr(d_u), nat.ptr(d_i), nat.ptr(d_r),
                                           prm.n_factors, nat.stream(), C.byref(plan)))
-    ur, ir = even_ranges(n_users, world), even_ranges(n_items, world)
     (u0, u1), (i0, i1) = ur[rank], ir[rank]
     try:
         cur = 0
@@ -430,8 +428,8 @@ def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0, stats=None):
                                                  u0, u1, i0, i1, nat.stream()))
             cur ^= 1
             if world > 1:
-                _all_gather_rows(dist, pu[cur], ur, rank)
-                _all_gather_rows(dist, qi[cur], ir, rank)
+                dist.all_gather_into_tensor(pu[cur], pu[cur][rank * per_u:(rank + 1) * per_u])
+                dist.all_gather_into_tensor(qi[cur], qi[cur][rank * per_i:(rank + 1) * per_i])
         nat.check(lib.sb2_nmf_plan_status(plan, nat.stream()))
         if stats is not None:
             torch.cuda.synchronize()
@@ -440,4 +438,4 @@ def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0, stats=None):
             stats["epochs_s"] = time.perf_counter() - t0
     finally:
         lib.sb2_nmf_plan_destroy(plan)
-    return pu[cur].cpu().numpy(), qi[cur].cpu().numpy(), bu.cpu().numpy(), bi.cpu().numpy()
+    return pu[cur][:n_users].cpu().numpy(), qi[cur][:n_items].cpu().numpy(), bu.cpu().numpy(), bi.cpu().numpy()

@@ -119,11 +119,11 @@ def test_sim_row_ranges_cover_and_align():
             assert hi == lo2 and lo % 256 == 0 and lo <= hi
 
 
-def test_even_ranges():
-    for n, w in ((10, 3), (480000, 8), (5, 8), (17700, 4)):
-        rs = D.even_ranges(n, w)
-        assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
-        assert max(hi - lo for lo, hi in rs) - min(hi - lo for lo, hi in rs) <= 1
+def test_block_ranges():
+    for n, w in ((10, 3), (480000, 8), (5, 8), (17700, 4), (8, 8)):
+        per, rs = D.block_ranges(n, w)
+        assert per * w >= n and rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert all(hi - lo <= per for lo, hi in rs) and all(lo == min(r * per, n) for r, (lo, hi) in enumerate(rs))
 
 
 def test_sim_tri_ranges_balance_and_exchange_plan():
@@ -179,25 +179,25 @@ def _gather_worker(rank, port, out_dir):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=2)
-    n, f = 11, 3
+    dist.init_process_group("gloo", rank=rank, world_size=3)
+    n, f = 10, 3                                   # 10 rows over 3 ranks: blocks of 4 (4 + 4 + 2), buffer padded to 12
     truth = torch.arange(n * f, dtype=torch.float64).reshape(n, f)
-    ranges = D.even_ranges(n, 2)
+    per, ranges = D.block_ranges(n, 3)
     lo, hi = ranges[rank]
-    full = torch.full((n, f), -1.0, dtype=torch.float64)
-    full[lo:hi] = truth[lo:hi]                     # what one NMF epoch leaves on this rank: only its own rows
-    D._all_gather_rows(dist, full, ranges, rank)
-    np.save(os.path.join(out_dir, "g%d.npy" % rank), full.numpy())
+    full = torch.full((per * 3, f), -1.0, dtype=torch.float64)
+    full[lo:hi] = truth[lo:hi]                     # what one NMF epoch leaves on this rank: only its own block
+    dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])   # in place, as nmf_fit_sharded does
+    np.save(os.path.join(out_dir, "g%d.npy" % rank), full[:n].numpy())
     dist.destroy_process_group()
 
 
-def test_nmf_all_gather_rows_two_ranks(tmp_path):
-    """The per-epoch exchange of the sharded NMF (uneven ranges): every rank ends up with every row."""
+def test_nmf_in_place_block_all_gather_three_ranks(tmp_path):
+    """The per-epoch exchange of the sharded NMF (uneven last block, padded buffer): every rank ends up with every row."""
     import torch.multiprocessing as mp
     port = 33500 + (os.getpid() % 2000)
-    mp.spawn(_gather_worker, args=(port, str(tmp_path)), nprocs=2, join=True)
-    want = np.arange(33, dtype=np.float64).reshape(11, 3)
-    for r in range(2):
+    mp.spawn(_gather_worker, args=(port, str(tmp_path)), nprocs=3, join=True)
+    want = np.arange(30, dtype=np.float64).reshape(10, 3)
+    for r in range(3):
         assert np.array_equal(np.load(os.path.join(str(tmp_path), "g%d.npy" % r)), want)
 
 

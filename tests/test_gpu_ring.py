@@ -267,3 +267,73 @@ def test_ring_processes_over_nvlink(tmp_path, algo_name):
     rg, mg = _scores(outs[0]["est"], tr_)
     r1, _ = _scores(est1, tr_)
     assert abs(rw - rg) <= RMSE_TOL and abs(mw - mg) <= RMSE_TOL, (rw, rg, r1)
+
+
+# ---- the paths that shard without a per-step exchange, as real processes --------------------------------------------
+def _sharded_worker(rank, world, port, out_dir):
+    import json
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from surprise_b200 import similarities as sims
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    out = {}
+    d = synth.ratings(9000, 3000, 500_000, step=0.5, seed=9, holdout=0.0)
+    u, i, r = d["train"]
+    ts = sb.Trainset.from_coo(u, i, r, d["n_users"], d["n_items"], (0.5, 5.0), 0)
+    yr = ts.user_csr()
+    mu = float(ts.global_mean)
+    rng = np.random.RandomState(1)
+    bx, by = rng.normal(0, .3, ts.n_items), rng.normal(0, .3, ts.n_users)
+    for path in ("digit", "general"):
+        os.environ["SB2_SIM_PATH"] = path
+        for kind in ("cosine", "pearson", "pearson_baseline"):
+            kw = dict(global_mean=mu, x_biases=bx, y_biases=by, shrinkage=100) if kind == "pearson_baseline" else {}
+            _, _, full = D.sim_build_sharded(dist, kind, ts.n_items, yr, 1, gather=True, **kw)   # CSR broadcast from rank 0
+            ref = sims.build_device(kind, ts.n_items, yr, 1, **kw)
+            out["sim_%s_%s" % (path, kind)] = bool(torch.equal(full, ref))
+    os.environ.pop("SB2_SIM_PATH")
+    # k-NN estimates with the matrix left sharded == estimates on the full matrix
+    px = rng.randint(-1, ts.n_items, 20000).astype(np.int32); py = rng.randint(0, ts.n_users, 20000).astype(np.int32)
+    b, e, block = D.sim_build_sharded(dist, "msd", ts.n_items, yr, 1)
+    got = D.knn_predict_sharded(dist, block, b, e, ts.n_items, px, py, yr, 40, 1)
+    full = sims.build_device("msd", ts.n_items, yr, 1)
+    ref = D.knn_predict_sharded(None, full, 0, ts.n_items, ts.n_items, px, py, yr, 40, 1)
+    out["knn_sharded"] = bool(all(np.array_equal(a, c) for a, c in zip(got, ref)))
+    # NMF: accumulators sharded, in-place block all-gather per epoch: bit-identical to the single-GPU fit
+    d2 = synth.ratings(10001, 1999, 600_000, seed=3, holdout=0.0)
+    u2, i2, r2 = d2["train"]
+    ts2 = sb.Trainset.from_coo(u2, i2, r2, d2["n_users"], d2["n_items"])
+    uu, ii, rr = ts2.coo()
+    pu0 = rng.uniform(0, 1, (ts2.n_users, 15)); qi0 = rng.uniform(0, 1, (ts2.n_items, 15))
+    for biased in (0, 1):
+        prm = nat.NmfParams(n_factors=15, n_epochs=4, biased=biased, reserved=0, global_mean=float(ts2.global_mean),
+                            reg_pu=.06, reg_qi=.06, reg_bu=.02, reg_bi=.02, lr_bu=.005, lr_bi=.005)
+        got = D.nmf_fit_sharded(dist, ts2.n_users, ts2.n_items, uu, ii, rr, prm, pu0, qi0)
+        ref = D.nmf_fit_sharded(None, ts2.n_users, ts2.n_items, uu, ii, rr, prm, pu0, qi0)
+        out["nmf_biased%d" % biased] = bool(all(np.array_equal(a, c) for a, c in zip(got, ref)))
+    with open(os.path.join(out_dir, "sharded_r%d.json" % rank), "w") as fh:
+        json.dump(out, fh)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_similarity_knn_nmf_processes(tmp_path):
+    """Row-sharded similarity build (both implementations, rating CSR broadcast over NCCL, symmetric shards + transpose
+    exchange), k-NN estimates on the sharded matrix, NMF with sharded accumulators: every rank's result must equal
+    the single-GPU result bit for bit."""
+    import json
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 36500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for g in range(world):
+        with open(os.path.join(str(tmp_path), "sharded_r%d.json" % g)) as fh:
+            res = json.load(fh)
+        assert all(res.values()), (g, res)
