@@ -183,6 +183,14 @@ int sb2_svd_ring_ipc_handle(const sb2_svd_plan* plan, unsigned char* handle64);
 int sb2_svd_ring_connect_ipc(sb2_svd_plan* plan, const unsigned char* left64, const unsigned char* right64);
 int sb2_svd_ring_connect_local(sb2_svd_plan* plan, sb2_svd_plan* left, sb2_svd_plan* right);
 int sb2_svd_ring_epoch_dev(sb2_svd_plan* plan, int phase, float* exchange, void* stream);
+/* All ranks of a ring in ONE process on ONE GPU (the single-GPU tests of the ring): plans[0 .. n) are the ranks
+ * 0 .. n-1 (n <= 4), connected with sb2_svd_ring_connect_local.  Kernels that wait for one another must never be
+ * issued as separate launches on one GPU, so all ranks run as one launch of n x B co-resident CTAs -- the same
+ * kernel body, the "peer" buffers being the other ranks' buffers in the same memory.  sb2_svd_ring_run_local: n_epochs
+ * SVD epochs; sb2_svd_ring_epoch_local: phase 0 of one SVD++ epoch for every rank (exchange[g]: rank g's partial
+ * sums; add them up, then call sb2_svd_ring_epoch_dev(plans[g], 1, sum) per rank). */
+int sb2_svd_ring_run_local(sb2_svd_plan** plans, int n_plans, int n_epochs, void* stream);
+int sb2_svd_ring_epoch_local(sb2_svd_plan** plans, int n_plans, float** exchange, void* stream);
 int sb2_svd_ring_info(const sb2_svd_plan* plan, int64_t* n_users_local, int64_t* n_items_local,
                       int64_t* n_ratings_local, int* row_stride);
 /* Per-CTA counters of the last run, cycles_host[n_blocks][8] (n_blocks from sb2_svd_plan_grid): SM cycles in

@@ -68,6 +68,8 @@ SIGNATURES = {
     "sb2_svd_ring_connect_ipc": (_int, [_vp, _vp, _vp]),
     "sb2_svd_ring_connect_local": (_int, [_vp, _vp, _vp]),
     "sb2_svd_ring_epoch_dev": (_int, [_vp, _int, _vp, _vp]),
+    "sb2_svd_ring_run_local": (_int, [_vp, _int, _int, _vp]),
+    "sb2_svd_ring_epoch_local": (_int, [_vp, _int, _vp, _vp]),
     "sb2_svd_ring_info": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "sb2_svd_plan_profile": (_int, [_vp, _vp]),
     "sb2_svdpp_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

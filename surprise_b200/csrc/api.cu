@@ -84,6 +84,8 @@ int64_t svd_plan_bytes_per_update(const sb2_svd_plan* p);
 void svd_plan_grid(const sb2_svd_plan* p, int* b, int* w);
 int svd_plan_status(sb2_svd_plan* p, cudaStream_t st);
 int svd_ring_epoch_dev(sb2_svd_plan* p, int phase, float* xch, cudaStream_t st);
+int svd_ring_run_local(sb2_svd_plan** plans, int n, int n_epochs, cudaStream_t st);
+int svd_ring_epoch_local(sb2_svd_plan** plans, int n, float** xch, cudaStream_t st);
 int svd_ring_ipc_handle(const sb2_svd_plan* p, unsigned char* out64);
 int svd_ring_connect_ipc(sb2_svd_plan* p, const unsigned char* left64, const unsigned char* right64);
 int svd_ring_connect_local(sb2_svd_plan* p, sb2_svd_plan* left, sb2_svd_plan* right);
@@ -407,6 +409,20 @@ int sb2_svd_ring_connect_local(sb2_svd_plan* plan, sb2_svd_plan* left, sb2_svd_p
         return SB2_ERR_INVALID;
     }
     return svd_ring_connect_local(plan, left, right);
+}
+int sb2_svd_ring_run_local(sb2_svd_plan** plans, int n_plans, int n_epochs, void* stream) {
+    if (!plans) {
+        set_error("svd_ring_run_local: null plans");
+        return SB2_ERR_INVALID;
+    }
+    return svd_ring_run_local(plans, n_plans, n_epochs, (cudaStream_t)stream);
+}
+int sb2_svd_ring_epoch_local(sb2_svd_plan** plans, int n_plans, float** exchange, void* stream) {
+    if (!plans || n_plans < 1 || n_plans > 4) {
+        set_error("svd_ring_epoch_local: 1..4 plans");
+        return SB2_ERR_INVALID;
+    }
+    return svd_ring_epoch_local(plans, n_plans, exchange, (cudaStream_t)stream);
 }
 int sb2_svd_ring_epoch_dev(sb2_svd_plan* plan, int phase, float* exchange, void* stream) {
     return svd_ring_epoch_dev(plan, phase, exchange, (cudaStream_t)stream);

@@ -424,11 +424,10 @@ __host__ __device__ constexpr int dsgd_threads(int g) { return g >= 16 ? 512 : 2
 // its updates in the same fixed order), but a cell costs its dependency chain (max degree x one update latency)
 // or its work / n_warps, whichever is longer, not (number of waves) x (slowest warp of the wave + barrier).
 template <int G, int CH, bool SU, bool SI, bool BIASED, bool PP, bool DEP = false>
-__global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const DsgdArgs a) {
+__device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
     extern __shared__ __align__(16) float smem_f[];
     const int B = a.B, W = a.W, FP = a.FP, F4 = a.FP >> 2;
     const int US = a.US, U4 = a.US >> 2;  // user rows: US floats ([p] or [p | z | g])
-    const int ub = blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int gid = tid / G, gl = tid % G;
     const int gid0 = (tid & ~31) / G;  // first lane-group of this warp
@@ -780,6 +779,27 @@ __global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const Dsgd
             if (PP) __stcg(a.cnt + ub + (size_t)l * B, cnt_s[l]);
         }
     }
+}
+
+template <int G, int CH, bool SU, bool SI, bool BIASED, bool PP, bool DEP = false>
+__global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_kernel(const DsgdArgs a) {
+    dsgd_body<G, CH, SU, SI, BIASED, PP, DEP>(a, blockIdx.x);
+}
+
+// All ranks of a ring in ONE launch (tests on a single GPU): the grid is n x B CTAs, CTA b works as CTA b % B of
+// rank b / B with that rank's arguments -- exactly the code of a real rank, the "peer" buffers simply being the other
+// ranks' slabs in the same memory.  Kernels that wait for each other must not be issued as separate launches on one
+// GPU (nothing guarantees that they run at the same time); one launch whose CTAs are all resident does.  B is a
+// multiple of the cluster size, so clusters never straddle ranks.
+constexpr int DSGD_MAX_VIRTUAL = 4;
+struct DsgdMulti {
+    DsgdArgs r[DSGD_MAX_VIRTUAL];
+};
+template <int G, int CH, bool BIASED, bool PP>
+__global__ void __launch_bounds__(dsgd_threads(G), 1) dsgd_svd_multi_kernel(const DsgdMulti m) {
+    const int B = m.r[0].B;
+    const int rank = blockIdx.x / B;
+    dsgd_body<G, CH, true, true, BIASED, PP, false>(m.r[rank], blockIdx.x - rank * B);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1669,6 +1689,72 @@ int svd_plan_run(sb2_svd_plan* p, int n_epochs, cudaStream_t st) {
     return SB2_OK;
 }
 
+// ---- all ranks of a ring in one launch on one GPU (sb2_svd_ring_run_local: single-GPU tests of the ring) ------------
+typedef void (*dsgd_multi_kernel_t)(const DsgdMulti);
+static dsgd_multi_kernel_t dsgd_multi_kernel(const sb2_svd_plan* p) {
+#define SB2_MULTI_CASE(g, ch)                                                                                   \
+    if (p->G == g && p->CH == ch) {                                                                             \
+        if (p->with_yj) return dsgd_svd_multi_kernel<g, ch, true, true>;                                        \
+        return p->prm.biased ? dsgd_svd_multi_kernel<g, ch, true, false> : dsgd_svd_multi_kernel<g, ch, false, false>; \
+    }
+    SB2_MULTI_CASE(1, 1) SB2_MULTI_CASE(1, 2) SB2_MULTI_CASE(1, 3) SB2_MULTI_CASE(1, 4) SB2_MULTI_CASE(2, 3) SB2_MULTI_CASE(2, 4)
+    SB2_MULTI_CASE(4, 3) SB2_MULTI_CASE(4, 4) SB2_MULTI_CASE(8, 3) SB2_MULTI_CASE(8, 4)
+#undef SB2_MULTI_CASE
+    return nullptr;
+}
+
+// plans[0 .. n): the ranks 0 .. n-1 of one ring, created in this process on the current device and connected with
+// sb2_svd_ring_connect_local.  Runs n_epochs epochs of all of them as ONE kernel launch.
+int svd_ring_run_local(sb2_svd_plan** plans, int n, int n_epochs, cudaStream_t st) {
+    if (n < 1 || n > DSGD_MAX_VIRTUAL || n_epochs <= 0) {
+        set_error("svd_ring_run_local: 1..%d ranks, n_epochs > 0", DSGD_MAX_VIRTUAL);
+        return SB2_ERR_INVALID;
+    }
+    sb2_svd_plan* p0 = plans[0];
+    DsgdMulti m;
+    memset(&m, 0, sizeof(m));
+    size_t smem = 0;
+    for (int g = 0; g < n; ++g) {
+        sb2_svd_plan* p = plans[g];
+        if (!p || p->P != n || p->rank != g || p->B != p0->B || p->C != p0->C || p->G != p0->G || p->CH != p0->CH ||
+            p->W != p0->W || p->with_yj != p0->with_yj || !p->stage_u || !p->stage_i || p->dep_mode || !p->fast) {
+            set_error("svd_ring_run_local: plans must be the ranks 0..n-1 of one ring with both blocks staged in shared memory");
+            return SB2_ERR_INVALID;
+        }
+        SB2_TRY(fill_args(p, m.r[g]));
+        m.r[g].n_epochs = n_epochs; m.r[g].s_begin = 0; m.r[g].s_end = p->P * p->B;
+        smem = std::max(smem, p->smem);
+    }
+    dsgd_multi_kernel_t kern = dsgd_multi_kernel(p0);
+    if (!kern) {
+        set_error("svd_ring_run_local: no single-launch kernel for %d lanes x %d chunks", p0->G, p0->CH);
+        return SB2_ERR_UNSUPPORTED;
+    }
+    SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, p0->C > 8 ? 1 : 0));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    dsgd_launch_config(p0, n * p0->B, &cfg, attr, st);
+    cfg.dynamicSmemBytes = smem;
+    if (p0->C > 1) {   // every CTA of every rank must be resident at once
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kern, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            max_clusters = 0;
+        }
+        if (max_clusters * p0->C < n * p0->B) {
+            set_error("svd_ring_run_local: %d x %d CTAs are not co-resident on this GPU (%d clusters of %d fit)", n,
+                      p0->B, max_clusters, p0->C);
+            return SB2_ERR_UNSUPPORTED;
+        }
+    }
+    void* args[] = {(void*)&m};
+    SB2_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, args));
+    launch_counter()++;
+    for (int g = 0; g < n; ++g) plans[g]->E_done += n_epochs * n;
+    return SB2_OK;
+}
+
 // One SVD++ epoch of a ring, in two halves around the caller's all-reduce of xch (n_items x (FP + 1) fp32, DEVICE):
 //   phase 0: refresh z_u of the rank's users from the (replicated) y_j, run the epoch's P sub-epochs, write the
 //            rank's partial [sum_u g_u | sum_u cnt_u] per item into xch;
@@ -1697,6 +1783,28 @@ int svd_ring_epoch_dev(sb2_svd_plan* p, int phase, float* xch, cudaStream_t st) 
     svdpp_item_partial_kernel<<<(unsigned)ceil_div(p->n_items * 32, 256), 256, 0, st>>>(p->n_items, p->FP, p->i_ptr,
                                                                                         p->iu_idx, p->pu, p->cnt, xch);
     SB2_LAUNCH_CHECK();
+    return SB2_OK;
+}
+
+// phase 0 of svd_ring_epoch_dev for all ranks of a ring in this process, the P sub-epochs as one launch
+int svd_ring_epoch_local(sb2_svd_plan** plans, int n, float** xch, cudaStream_t st) {
+    for (int g = 0; g < n; ++g) {
+        sb2_svd_plan* p = plans[g];
+        if (!p || !p->with_yj || !xch || !xch[g]) {
+            set_error("svd_ring_epoch_local: SVD++ plans and exchange buffers required");
+            return SB2_ERR_INVALID;
+        }
+        svdpp_user_refresh_kernel<<<(unsigned)ceil_div(p->nu_loc * 32, 256), 256, 0, st>>>(p->nu_loc, p->FP, p->u_ptr,
+                                                                                           p->ui_idx, p->yj, p->isq, p->pu, p->cnt);
+        SB2_LAUNCH_CHECK();
+    }
+    SB2_TRY(svd_ring_run_local(plans, n, 1, st));
+    for (int g = 0; g < n; ++g) {
+        sb2_svd_plan* p = plans[g];
+        svdpp_item_partial_kernel<<<(unsigned)ceil_div(p->n_items * 32, 256), 256, 0, st>>>(p->n_items, p->FP, p->i_ptr,
+                                                                                            p->iu_idx, p->pu, p->cnt, xch[g]);
+        SB2_LAUNCH_CHECK();
+    }
     return SB2_OK;
 }
 

@@ -1,9 +1,10 @@
 """The multi-rank DSGD ring (SVD / SVD++ sharded by user, item blocks handed rank -> rank inside the kernel).
 
-On ONE GPU the ranks of a ring are driven from one process on separate streams (sb2_svd_ring_connect_local): the
-kernels of all ranks are co-resident and exchange item blocks through the very same code path as over NVLink
-(peer pointer stores + system-scope flags), so the schedule, the mailboxes and the credits are exercised by the
-driver's single-GPU test run.  With >= 2 GPUs the same fits run as real processes over NCCL + cudaIpc
+On ONE GPU all ranks of a ring run as ONE kernel launch (sb2_svd_ring_run_local: n x B co-resident CTAs, CTA b
+working as CTA b % B of rank b / B with that rank's arguments): the same kernel body exchanges item blocks through
+the very same code path as over NVLink (stores through "peer" pointers + system-scope flags + credits), so the
+schedule and the mailboxes are exercised by a single-GPU test run -- without ever issuing kernels that wait for one
+another as separate launches.  With >= 2 GPUs the same fits run as real processes over NCCL + cudaIpc
 (tests marked with the device-count skip).  Parity: held-out RMSE / MAE within 0.005 of the sequential oracle, and
 a conflict-free input (order-independent SGD) reproduced to fp32 rounding.
 """
@@ -59,30 +60,24 @@ def virtual_ring_fit(world, n_users, n_items, u, i, r, prm, pu0, qi0, yj0=None, 
                 nat.check(lib.sb2_svd_ring_connect_local(plans[g], plans[left], plans[right]))
             nat.check(lib.sb2_svd_plan_reset_dev(plans[g], nat.ptr(d_pu0), nat.ptr(d_qi0), nat.ptr(d_yj0), nat.stream()))
         torch.cuda.synchronize()
-        streams = [torch.cuda.Stream() for _ in range(world)]
-        sp = lambda s: C.c_void_p(s.cuda_stream)
+        arr = (C.c_void_p * world)(*[p.value for p in plans])
         if not with_yj:
-            for g in range(world):
-                nat.check(lib.sb2_svd_plan_run(plans[g], n_epochs, sp(streams[g])))
+            nat.check(lib.sb2_svd_ring_run_local(arr, world, n_epochs, nat.stream()))
         else:
             stride = C.c_int()
             lib.sb2_svd_ring_info(plans[0], None, None, None, C.byref(stride))
             xch = [torch.empty((n_items, stride.value + 1), dtype=torch.float32, device="cuda") for _ in range(world)]
+            xarr = (C.c_void_p * world)(*[t.data_ptr() for t in xch])
             for _ in range(n_epochs):
-                for g in range(world):
-                    nat.check(lib.sb2_svd_ring_epoch_dev(plans[g], 0, nat.ptr(xch[g]), sp(streams[g])))
-                torch.cuda.synchronize()
+                nat.check(lib.sb2_svd_ring_epoch_local(arr, world, xarr, nat.stream()))
                 total = torch.stack(xch).sum(0)          # what the NCCL all-reduce does across processes
                 for g in range(world):
-                    xch[g].copy_(total)
-                torch.cuda.synchronize()
-                for g in range(world):
-                    nat.check(lib.sb2_svd_ring_epoch_dev(plans[g], 1, nat.ptr(xch[g]), sp(streams[g])))
-                torch.cuda.synchronize()
+                    nat.check(lib.sb2_svd_ring_epoch_dev(plans[g], 1, nat.ptr(total), nat.stream()))
+        torch.cuda.synchronize()
         parts = {k: [] for k in ("pu", "qi", "bu", "bi")}
         yj = None
         for g in range(world):
-            nat.check(lib.sb2_svd_plan_status(plans[g], sp(streams[g])))
+            nat.check(lib.sb2_svd_plan_status(plans[g], nat.stream()))
             nu, ni = C.c_int64(), C.c_int64()
             lib.sb2_svd_ring_info(plans[g], C.byref(nu), C.byref(ni), None, None)
             assert nu.value == D.local_rows(n_users, g, world) and ni.value == D.local_rows(n_items, g, world)
