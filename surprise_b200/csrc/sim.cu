@@ -604,7 +604,7 @@ __global__ void sim_visits_kernel(int64_t n_y, const int64_t* __restrict__ y_ptr
 //           independent of the sparsity; exact for cosine / msd / pearson on grid ratings, 1e-9-class for
 //           pearson_baseline; needs non-negative ratings on a 1/d grid and unique (x, y) pairs.
 //   general (sim_general.cu): the reference's own loop nest on the CUDA cores, fp64, bit-identical to the reference for
-//           ANY input.  Cost ~ sum_y |yr[y]|^2 co-ratings (~1.8e10 / s on a B200 at n_x = 27k).
+//           ANY input.  Cost ~ sum_y |yr[y]|^2 co-ratings (~2.1e10 / s on a B200 at n_x = 27k).
 // rating_denom == 0 (no grid / negative ratings) and duplicated pairs (detected by the pack kernel) always take the
 // general path: everything the reference accepts is computed, nothing is rejected.  Otherwise the cheaper one by the
 // cost model below runs; pearson_baseline prefers the general path unless the digit path is clearly (1.5x) faster,
@@ -632,7 +632,7 @@ static int sim_dispatch(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr
         const double rows = (double)(row_end - row_begin), frac = rows / (double)n_x;
         // general: co-ratings of the shard's rows + zeroing / reading the 32-byte column records of every row
         const double keep = upper ? 1.0 - ((double)row_begin + 0.5 * rows) / (double)n_x : 1.0;  // columns >= row_begin
-        const double t_general = frac * keep * visits / 1.5e10 + rows * (double)n_x * 64.0 / 3.0e12 + 2e-4;
+        const double t_general = frac * keep * visits / 2.0e10 + rows * (double)n_x * 64.0 / 3.0e12 + 2e-4;
         // digit: accumulators x tiles x k at the measured 3.6 POP/s issued, + packing the dense panels
         const int n_acc = kind == SB2_SIM_PEARSON_BASELINE ? 30 : kind == SB2_SIM_PEARSON ? 6 : 4;
         const double n_pad = (double)round_up(n_x, 256), k_pad = (double)round_up(std::max<int64_t>(n_y, 1), 128);

@@ -39,6 +39,12 @@ struct GenArgs {
     const int* y_of;        // yr segment of every entry
     const uint8_t* occ;     // occurrence index of the entry among the entries with the same (x, y)
     int max_occ;
+    // x-major sweep descriptors (no duplicated pairs): for the p-th entry of the x-major order, the yr segment it
+    // lies in [xm_b, xm_b + xm_len) and its value
+    const int64_t* xm_b;
+    const int* xm_len;
+    const double* xm_r;     // the row entry's value (rating, or deviation for pearson_baseline)
+    const double* val;      // per entry of the yr CSR: the rating, or (pearson_baseline) its deviation
     int min_support;
     double mu, shrinkage;
     const double* bx;
@@ -227,6 +233,174 @@ __global__ void __launch_bounds__(256) sim_rows_kernel(const GenArgs a) {
     }
 }
 
+// x-major sweep descriptors: one coalesced stream per row instead of the dependent chain
+// x_ent -> y_of -> y_ptr -> entries in front of every sweep
+__global__ void gen_desc_kernel(int64_t nnz, const int* __restrict__ x_ent, const int* __restrict__ y_of,
+                                const int64_t* __restrict__ y_ptr, const double* __restrict__ val,
+                                int64_t* __restrict__ xm_b, int* __restrict__ xm_len, double* __restrict__ xm_r) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const int e = x_ent[p];
+    const int y = y_of[e];
+    const int64_t b = y_ptr[y];
+    xm_b[p] = b;
+    xm_len[p] = (int)(y_ptr[y + 1] - b);
+    xm_r[p] = val[e];
+}
+
+// pearson_baseline: deviation of every entry, r - ((mu + b_y) + b_x), the reference's operations in the reference's
+// order (similarities.pyx:337-340); it depends on the entry alone
+__global__ void gen_dev_kernel(int64_t nnz, const int32_t* __restrict__ x_idx, const int* __restrict__ y_of,
+                               const double* __restrict__ r, double mu, const double* __restrict__ bx,
+                               const double* __restrict__ by, double* __restrict__ dev) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nnz) return;
+    const double pb = __dadd_rn(mu, by[y_of[c]]);
+    dev[c] = __dsub_rn(r[c], __dadd_rn(pb, bx[x_idx[c]]));
+}
+
+// The same accumulation as sim_rows_kernel for inputs WITHOUT duplicated pairs (one entry of the row per y, every
+// column at most once per sweep), with the memory latencies taken off the critical path of a sweep:
+//   * the sweep descriptors of a row (segment start / length, the row's value) arrive in coalesced chunks through
+//     shared memory instead of the dependent chain x_ent -> y_of -> y_ptr in front of every sweep;
+//   * the (x, value) entries of the sweeps stream through a shared-memory ring filled by cp.async, GEN_RING sweeps
+//     ahead;
+//   * pearson_baseline: the deviations r - ((mu + b_y) + b_x) depend on the ENTRY only, so they are computed once per
+//     entry (gen_dev_kernel, the reference's operation order) and the accumulation becomes cosine's on deviations
+//     -- no gather of b_x inside the sweeps.
+// What remains per co-rating is the read-modify-write of one 32-byte column record (48 B for pearson) in the CTA's
+// scratch row: ~1.3 TB/s of random 32-byte-sector DRAM traffic at the ml-20M shape (ncu: DRAM bytes ~= 64 B per
+// co-rating, L2 hit rate 55 %), which is what bounds the kernel.  Keeping the records of a column TILE in shared
+// memory instead (one CTA per SM, every tile re-reading the row's segments) was measured slower: 0.20 s against 0.14 s
+// for cosine at that shape -- with one resident CTA per SM the per-sweep barrier and shared-memory latencies are not
+// hidden.
+constexpr int GEN_CHUNK = 128;
+constexpr int GEN_RING = 8;   // sweeps in flight
+template <int KIND>
+__global__ void __launch_bounds__(256, 4) sim_rows_fast_kernel(const GenArgs a) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int64_t n_x = a.n_x;
+    constexpr int NREC = KIND == 2 ? 6 : 4;
+    constexpr int I_SQI = 1, I_SQJ = 2, I_SI = 3, I_SJ = 4, I_FQ = NREC - 1;
+    __shared__ int64_t s_b[GEN_CHUNK];
+    __shared__ int s_len[GEN_CHUNK];
+    __shared__ double s_r[GEN_CHUNK];
+    __shared__ int s_x[GEN_RING][256];
+    __shared__ double s_rj[GEN_RING][256];
+    int min_sprt = a.min_support;
+    if (KIND == 3 && min_sprt < 2) min_sprt = 2;  // similarities.pyx:334
+    double* REC = a.scratch + (size_t)blockIdx.x * a.scratch_stride;   // this CTA's row of column records
+    const int c0 = (int)a.col_begin, c1 = (int)n_x;
+    for (int64_t row = a.row_begin + blockIdx.x; row < a.row_end; row += gridDim.x) {
+        for (int64_t x = tid; x < (int64_t)(c1 - c0) * NREC / 2; x += nthr)
+            reinterpret_cast<double2*>(REC)[x] = make_double2(0.0, 0.0);
+        // ri / rj: ratings -- or, for pearson_baseline, the precomputed deviations
+        auto visit = [&](double ri, int xj, double rj) {
+            double* R = REC + (size_t)(xj - c0) * NREC;
+            if (KIND == 2) {
+                double2 v0 = *reinterpret_cast<double2*>(R), v1 = *reinterpret_cast<double2*>(R + 2),
+                        v2 = *reinterpret_cast<double2*>(R + 4);
+                v0.x = __dadd_rn(v0.x, __dmul_rn(ri, rj));
+                v0.y = __dadd_rn(v0.y, __dmul_rn(ri, ri));
+                v1.x = __dadd_rn(v1.x, __dmul_rn(rj, rj));
+                v1.y = __dadd_rn(v1.y, ri);
+                v2.x = __dadd_rn(v2.x, rj);
+                v2.y += 1.0;
+                *reinterpret_cast<double2*>(R) = v0; *reinterpret_cast<double2*>(R + 2) = v1;
+                *reinterpret_cast<double2*>(R + 4) = v2;
+            } else {
+                double2 v0 = *reinterpret_cast<double2*>(R), v1 = *reinterpret_cast<double2*>(R + 2);
+                if (KIND == 1) {
+                    const double d = __dsub_rn(ri, rj);
+                    v0.x = __dadd_rn(v0.x, __dmul_rn(d, d));
+                } else {
+                    v0.x = __dadd_rn(v0.x, __dmul_rn(ri, rj));
+                    v0.y = __dadd_rn(v0.y, __dmul_rn(ri, ri));
+                    v1.x = __dadd_rn(v1.x, __dmul_rn(rj, rj));
+                }
+                v1.y += 1.0;
+                *reinterpret_cast<double2*>(R) = v0; *reinterpret_cast<double2*>(R + 2) = v1;
+            }
+        };
+        const int64_t p_end = a.x_ptr[row + 1];
+        for (int64_t p0 = a.x_ptr[row]; p0 < p_end; p0 += GEN_CHUNK) {
+            const int nq = (int)(p_end - p0 < GEN_CHUNK ? p_end - p0 : GEN_CHUNK);
+            __syncthreads();   // the previous chunk's descriptors are no longer read; (first chunk) REC is zeroed
+            if (tid < nq) {
+                s_b[tid] = a.xm_b[p0 + tid]; s_len[tid] = a.xm_len[p0 + tid]; s_r[tid] = a.xm_r[p0 + tid];
+            }
+            __syncthreads();
+            // (x, r) of the sweeps stream through a ring of GEN_RING stages filled by cp.async: the entries of sweep
+            // q + GEN_RING - 1 are requested while sweep q is applied, so that the L2 latency (~4 sweeps long) is
+            // hidden with one CTA per SM.  Every thread copies and later reads its OWN slot: no barrier is needed
+            // between the copy and the read, only cp.async.wait_group.
+            auto request = [&](int q) {
+                if (q < nq && tid < s_len[q]) {
+                    const int st = q % GEN_RING;
+                    const int64_t c = s_b[q] + tid;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_x[st][tid])),
+                                 "l"(a.x_idx + c) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_rj[st][tid])),
+                                 "l"(a.val + c) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            for (int q = 0; q < GEN_RING - 1; ++q) request(q);
+            for (int q = 0; q < nq; ++q) {
+                request(q + GEN_RING - 1);
+                asm volatile("cp.async.wait_group %0;" ::"n"(GEN_RING - 1) : "memory");   // sweep q has landed
+                const double ri = s_r[q];
+                if (tid < s_len[q]) {
+                    const int xj = s_x[q % GEN_RING][tid];
+                    if (xj >= c0) visit(ri, xj, s_rj[q % GEN_RING][tid]);
+                }
+                for (int64_t c = s_b[q] + tid + nthr; c < s_b[q] + s_len[q]; c += nthr) {   // segments longer than the CTA
+                    const int xc = a.x_idx[c];
+                    if (xc >= c0) visit(ri, xc, a.val[c]);
+                }
+                __syncthreads();  // the next sweep may hit the same columns
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        // finalize (similarities.pyx:86-95 / :155-164 / :240-256 / :347-359); see sim_rows_kernel for why every row
+        // can evaluate both triangles itself
+        double* out = a.sim + (size_t)(row - a.row_begin) * n_x;
+        for (int xj = c0 + tid; xj < c1; xj += nthr) {
+            double s = 0.0;
+            const double* R = REC + (size_t)(xj - c0) * NREC;
+            const int fq = (int)R[I_FQ];
+            if (xj == row) {
+                s = 1.0;
+            } else if (fq >= min_sprt) {
+                const bool up = row < xj;
+                const double prods = R[0], sqi = up ? R[I_SQI] : R[I_SQJ], sqj = up ? R[I_SQJ] : R[I_SQI];
+                if (KIND == 0) {
+                    s = __ddiv_rn(prods, __dsqrt_rn(__dmul_rn(sqi, sqj)));
+                } else if (KIND == 1) {
+                    if (fq == 0) atomicExch(&a.status[G_ST_ZERODIV], 1);
+                    else s = __ddiv_rn(1.0, __dadd_rn(__ddiv_rn(prods, (double)fq), 1.0));
+                } else if (KIND == 2) {
+                    const double n = (double)fq;
+                    const double si = up ? R[I_SI] : R[I_SJ], sj = up ? R[I_SJ] : R[I_SI];
+                    const double num = __dsub_rn(__dmul_rn(n, prods), __dmul_rn(si, sj));
+                    const double denum = __dsqrt_rn(__dmul_rn(__dsub_rn(__dmul_rn(n, sqi), __dmul_rn(si, si)),
+                                                              __dsub_rn(__dmul_rn(n, sqj), __dmul_rn(sj, sj))));
+                    s = denum == 0.0 ? 0.0 : __ddiv_rn(num, denum);
+                } else {
+                    s = __ddiv_rn(prods, __dsqrt_rn(__dmul_rn(sqi, sqj)));
+                    const double fm1 = (double)(fq - 1);
+                    const double den = __dadd_rn(fm1, a.shrinkage);
+                    if (den == 0.0) atomicExch(&a.status[G_ST_ZERODIV], 1);
+                    else s = __dmul_rn(s, __ddiv_rn(fm1, den));
+                }
+            }
+            out[xj] = s;
+        }
+        __syncthreads();   // REC is zeroed for the next row only after every thread has read it
+    }
+}
+
 int sim_general_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, const int32_t* x_idx, const double* r,
                     int64_t nnz, int min_support, double global_mean, const double* x_biases, const double* y_biases,
                     double shrinkage, int64_t row_begin, int64_t row_end, bool upper, double* sim_out, cudaStream_t st) {
@@ -300,11 +474,37 @@ int sim_general_dev(int kind, int64_t n_x, int64_t n_y, const int64_t* y_ptr, co
     a.bx = x_biases; a.by = y_biases; a.row_begin = row_begin; a.row_end = row_end; a.sim = sim_out;
     a.col_begin = upper ? row_begin : 0;
     a.scratch = scratch_d.as<double>(); a.scratch_stride = stride; a.status = status_d.as<int>();
-    switch (kind) {
-        case 0: sim_rows_kernel<0><<<grid, 256, 0, st>>>(a); break;
-        case 1: sim_rows_kernel<1><<<grid, 256, 0, st>>>(a); break;
-        case 2: sim_rows_kernel<2><<<grid, 256, 0, st>>>(a); break;
-        default: sim_rows_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    DevBuf xmb_d, xml_d, xmr_d, xmp_d;
+    if (a.max_occ == 0 && nnz > 0) {
+        // no duplicated pair (the usual case): x-major sweep descriptors + the software-pipelined kernel
+        SB2_TRY(xmb_d.alloc(n1 * 8, st));
+        SB2_TRY(xml_d.alloc(n1 * 4, st));
+        SB2_TRY(xmr_d.alloc(n1 * 8, st));
+        const double* val = r;
+        if (kind == SB2_SIM_PEARSON_BASELINE) {
+            SB2_TRY(xmp_d.alloc(n1 * 8, st));
+            gen_dev_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, st>>>(nnz, x_idx, y_of_d.as<int>(), r, global_mean, x_biases,
+                                                                        y_biases, xmp_d.as<double>());
+            SB2_LAUNCH_CHECK();
+            val = xmp_d.as<double>();
+        }
+        gen_desc_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, st>>>(nnz, ent2_d.as<int>(), y_of_d.as<int>(), y_ptr, val,
+                                                                     xmb_d.as<int64_t>(), xml_d.as<int>(), xmr_d.as<double>());
+        SB2_LAUNCH_CHECK();
+        a.xm_b = xmb_d.as<int64_t>(); a.xm_len = xml_d.as<int>(); a.xm_r = xmr_d.as<double>(); a.val = val;
+        switch (kind) {
+            case 0: sim_rows_fast_kernel<0><<<grid, 256, 0, st>>>(a); break;
+            case 1: sim_rows_fast_kernel<1><<<grid, 256, 0, st>>>(a); break;
+            case 2: sim_rows_fast_kernel<2><<<grid, 256, 0, st>>>(a); break;
+            default: sim_rows_fast_kernel<3><<<grid, 256, 0, st>>>(a); break;
+        }
+    } else {
+        switch (kind) {
+            case 0: sim_rows_kernel<0><<<grid, 256, 0, st>>>(a); break;
+            case 1: sim_rows_kernel<1><<<grid, 256, 0, st>>>(a); break;
+            case 2: sim_rows_kernel<2><<<grid, 256, 0, st>>>(a); break;
+            default: sim_rows_kernel<3><<<grid, 256, 0, st>>>(a); break;
+        }
     }
     SB2_LAUNCH_CHECK();
     SB2_CUDA(cudaMemcpyAsync(status_h, status_d.p, sizeof(status_h), cudaMemcpyDeviceToHost, st));
