@@ -100,6 +100,14 @@ int sb2_baseline_als_dev(int64_t n_users, int64_t n_items, const int64_t* u_ptr,
 int sb2_baseline_als(int64_t n_users, int64_t n_items, const int64_t* u_ptr, const int32_t* ui_idx,
                      const double* u_r, const int64_t* i_ptr, const int32_t* iu_idx, const double* i_r,
                      double global_mean, int n_epochs, double reg_u, double reg_i, double* bu, double* bi);
+/* One half-epoch of baseline_als (optimize_baselines.pyx:41-46 items / :48-53 users) over the segments
+ * [seg_begin, seg_end) of one side's CSR: mine[s] = sum_{a in seg s} (r[a] - mu - other[idx[a]]) / (reg + |seg s|).
+ * The unit of the multi-rank ALS: every ordered sum is evaluated on exactly one rank (bit-identical to the
+ * single-GPU result), the caller all-gathers `mine` between the passes.  status_dev: DEVICE int, set to 1 where the
+ * reference would raise ZeroDivisionError. */
+int sb2_baseline_als_pass_dev(int64_t seg_begin, int64_t seg_end, const int64_t* ptr, const int32_t* idx, const double* r,
+                              const double* other, double* mine, double global_mean, double reg, int* status_dev,
+                              void* stream);
 int sb2_baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
                          const double* r, double global_mean, int n_epochs, double reg, double lr, double* bu,
                          double* bi, void* stream);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "sb2_gemm_u8_selftest_dev": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "sb2_baseline_als_dev": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _int, _dbl, _dbl, _vp, _vp, _vp]),
     "sb2_baseline_als": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _int, _dbl, _dbl, _vp, _vp]),
+    "sb2_baseline_als_pass_dev": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp]),
     "sb2_baseline_sgd_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _dbl, _int, _dbl, _dbl, _vp, _vp, _vp]),
     "sb2_baseline_sgd": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _dbl, _int, _dbl, _dbl, _vp, _vp]),
     "sb2_svd_fit_dev": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

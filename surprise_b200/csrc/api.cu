@@ -48,6 +48,8 @@ int rating_denominator_dev(const double* r, int64_t nnz, int* denom_out, cudaStr
 int baseline_als_dev(int64_t n_users, int64_t n_items, const int64_t* u_ptr, const int32_t* ui_idx, const double* u_r,
                      const int64_t* i_ptr, const int32_t* iu_idx, const double* i_r, double mu, int n_epochs,
                      double reg_u, double reg_i, double* bu, double* bi, cudaStream_t st);
+int baseline_als_pass_dev(int64_t seg_begin, int64_t seg_end, const int64_t* ptr, const int32_t* idx, const double* r,
+                          const double* other, double* mine, double mu, double reg, int* status_dev, cudaStream_t st);
 int baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
                      double mu, int n_epochs, double reg, double lr, double* bu, double* bi, cudaStream_t st);
 int nmf_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
@@ -228,6 +230,18 @@ int sb2_baseline_als(int64_t n_users, int64_t n_items, const int64_t* u_ptr, con
     SB2_TRY(download(bi, d_bi.p, (size_t)n_items, st));
     SB2_CUDA(cudaStreamSynchronize(st));
     return SB2_OK;
+}
+
+int sb2_baseline_als_pass_dev(int64_t seg_begin, int64_t seg_end, const int64_t* ptr, const int32_t* idx, const double* r,
+                              const double* other, double* mine, double global_mean, double reg, int* status_dev,
+                              void* stream) {
+    SB2_TRY(ensure_device());
+    if (!ptr || !idx || !r || !other || !mine || !status_dev || seg_begin < 0) {
+        set_error("baseline_als_pass: invalid argument");
+        return SB2_ERR_INVALID;
+    }
+    return baseline_als_pass_dev(seg_begin, seg_end, ptr, idx, r, other, mine, global_mean, reg, status_dev,
+                                 (cudaStream_t)stream);
 }
 
 int sb2_baseline_sgd_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,

@@ -24,8 +24,8 @@ enum { SEG_ZERODIV = 0 };
 // =================================================================================================
 __global__ void als_pass_kernel(int64_t n_seg, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                 const double* __restrict__ r, const double* other, double* mine, double mu,
-                                double reg, int* status) {
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                                double reg, int* status, int64_t seg_begin = 0) {
+    const int64_t s = seg_begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const int64_t b = ptr[s], e = ptr[s + 1];
     double dev = 0.0;
@@ -65,6 +65,19 @@ int baseline_als_dev(int64_t n_users, int64_t n_items, const int64_t* u_ptr, con
         set_error("float division");
         return SB2_ERR_ZERO_DIVISION;
     }
+    return SB2_OK;
+}
+
+// One half-epoch of baseline_als restricted to the segments [seg_begin, seg_end) -- the unit of the multi-rank ALS
+// (SURVEY.md 8e "baselines (ALS)": every ordered sum is evaluated by exactly one rank, the new biases are all-gathered
+// between the two passes of an epoch; surprise_b200/distributed.py baseline_als_sharded).  status_dev: one int,
+// set to 1 where the reference divides by zero.
+int baseline_als_pass_dev(int64_t seg_begin, int64_t seg_end, const int64_t* ptr, const int32_t* idx, const double* r,
+                          const double* other, double* mine, double mu, double reg, int* status_dev, cudaStream_t st) {
+    if (seg_end <= seg_begin) return SB2_OK;
+    als_pass_kernel<<<(unsigned)ceil_div(seg_end - seg_begin, 128), 128, 0, st>>>(seg_end, ptr, idx, r, other, mine, mu, reg,
+                                                                                  status_dev, seg_begin);
+    SB2_LAUNCH_CHECK();
     return SB2_OK;
 }
 

@@ -439,3 +439,41 @@ def nmf_fit_sharded(dist, n_users, n_items, u, i, r, prm, pu0, qi0, stats=None):
     finally:
         lib.sb2_nmf_plan_destroy(plan)
     return pu[cur][:n_users].cpu().numpy(), qi[cur][:n_items].cpu().numpy(), bu.cpu().numpy(), bi.cpu().numpy()
+
+
+def baseline_als_sharded(dist, trainset, n_epochs=10, reg_u=15.0, reg_i=10.0):
+    """baseline_als (optimize_baselines.pyx:14-54) over the ranks of `dist` (last row): per epoch the
+    item biases of item block g are evaluated on rank g (ordered sums over ir[i], needing all of bu), all-gathered in
+    place, then the same for the user biases.  Every ordered sum lives on one rank: (bu, bi) are bit-identical to the
+    single-GPU sb2_baseline_als_dev on every rank.  Returns float64 numpy arrays."""
+    from . import _native as nat
+    torch = nat.torch_cuda()
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    lib = nat.lib()
+    up, ui, ur = trainset.user_csr()
+    ip, iu, ir = trainset.item_csr()
+    d_up, d_ui, d_ur = nat.to_dev(up, np.int64), nat.to_dev(ui, np.int32), nat.to_dev(ur, np.float64)
+    d_ip, d_iu, d_ir = nat.to_dev(ip, np.int64), nat.to_dev(iu, np.int32), nat.to_dev(ir, np.float64)
+    n_users, n_items, mu = trainset.n_users, trainset.n_items, float(trainset.global_mean)
+    per_u, ru = block_ranges(n_users, world)
+    per_i, ri = block_ranges(n_items, world)
+    dev = nat.device()
+    bu = torch.zeros(per_u * world, dtype=torch.float64, device=dev)
+    bi = torch.zeros(per_i * world, dtype=torch.float64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    (u0, u1), (i0, i1) = ru[rank], ri[rank]
+    for _ in range(int(n_epochs)):
+        nat.check(lib.sb2_baseline_als_pass_dev(i0, i1, nat.ptr(d_ip), nat.ptr(d_iu), nat.ptr(d_ir), nat.ptr(bu), nat.ptr(bi),
+                                                mu, float(reg_i), nat.ptr(status), nat.stream()))
+        if world > 1:
+            dist.all_gather_into_tensor(bi, bi[rank * per_i:(rank + 1) * per_i])
+        nat.check(lib.sb2_baseline_als_pass_dev(u0, u1, nat.ptr(d_up), nat.ptr(d_ui), nat.ptr(d_ur), nat.ptr(bi), nat.ptr(bu),
+                                                mu, float(reg_u), nat.ptr(status), nat.stream()))
+        if world > 1:
+            dist.all_gather_into_tensor(bu, bu[rank * per_u:(rank + 1) * per_u])
+    if world > 1:
+        dist.all_reduce(status, op=dist.ReduceOp.MAX)
+    if int(status.item()):
+        raise ZeroDivisionError("float division")
+    return bu[:n_users].cpu().numpy(), bi[:n_items].cpu().numpy()

@@ -310,16 +310,30 @@ def _sharded_worker(rank, world, port, out_dir):
         got = D.nmf_fit_sharded(dist, ts2.n_users, ts2.n_items, uu, ii, rr, prm, pu0, qi0)
         ref = D.nmf_fit_sharded(None, ts2.n_users, ts2.n_items, uu, ii, rr, prm, pu0, qi0)
         out["nmf_biased%d" % biased] = bool(all(np.array_equal(a, c) for a, c in zip(got, ref)))
+    # ALS baselines: segment ranges per rank, in-place all-gather between the two passes of an epoch
+    got = D.baseline_als_sharded(dist, ts2, 10, 15.0, 10.0)
+    ref = oracle.baseline_als(ts2.n_users, ts2.n_items, *ts2.user_csr(), *ts2.item_csr(), float(ts2.global_mean))
+    out["baseline_als"] = bool(np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]))
     with open(os.path.join(out_dir, "sharded_r%d.json" % rank), "w") as fh:
         json.dump(out, fh)
     dist.barrier()
     dist.destroy_process_group()
 
 
+def test_baseline_als_range_passes_bit_exact(u1, u1_golden):
+    """sb2_baseline_als_pass_dev (the unit of the multi-rank ALS) driven by baseline_als_sharded without a process
+    group: sha256(bu), sha256(bi) = the reference's goldens on the fixture."""
+    import hashlib
+    ts, _ = u1
+    bu, bi = D.baseline_als_sharded(None, ts, 10, 15.0, 10.0)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(bu) == u1_golden["baseline_als"]["bu_sha256"] and sha(bi) == u1_golden["baseline_als"]["bi_sha256"]
+
+
 def test_sharded_similarity_knn_nmf_processes(tmp_path):
     """Row-sharded similarity build (both implementations, rating CSR broadcast over NCCL, symmetric shards + transpose
-    exchange), k-NN estimates on the sharded matrix, NMF with sharded accumulators: every rank's result must equal
-    the single-GPU result bit for bit."""
+    exchange), k-NN estimates on the sharded matrix, NMF with sharded accumulators, ALS baselines by segment ranges:
+    every rank's result must equal the single-GPU result / the oracle bit for bit."""
     import json
     import torch
     world = min(torch.cuda.device_count(), 4)
