@@ -538,6 +538,13 @@ def secondary_metrics(nat, dist, rank, world):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         bu, bi = algo.compute_baselines()
         torch.cuda.synchronize(); out["c3_baseline_als_s"] = time.perf_counter() - t0
+        if world > 1:   # the same baselines with the ordered sums sharded over the ranks (bit-identical)
+            D.baseline_als_sharded(dist, ts)
+            torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+            sbu, sbi = D.baseline_als_sharded(dist, ts)
+            torch.cuda.synchronize(); dist.barrier()
+            out["c3_baseline_als_sharded_s_from_host_csr"] = time.perf_counter() - t0
+            out["c3_baseline_als_sharded_bit_identical"] = bool(np.array_equal(sbu, bu) and np.array_equal(sbi, bi))
         yr = ts.user_csr()
         n_x, n_y = ts.n_items, ts.n_users
         kw = dict(global_mean=float(ts.global_mean), x_biases=bi, y_biases=bu, shrinkage=100)
