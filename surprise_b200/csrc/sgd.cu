@@ -26,6 +26,9 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -1197,6 +1200,49 @@ static void free_async(void* q, cudaStream_t st) {
     if (q) cudaFreeAsync(q, st);
 }
 
+// Ring slabs and peer mappings are cached for the life of the process: cudaMalloc / cudaFree of an IPC-exported
+// allocation and cudaIpcOpenMemHandle / cudaIpcCloseMemHandle cost milliseconds to hundreds of milliseconds, which
+// a fit of 12 ms cannot afford per call.  A destroyed plan returns its slab to the free list; a new plan takes a free
+// slab that is large enough (plans alive at the same time -- the ranks of a single-process test ring -- get distinct
+// slabs); a peer's handle is opened once and the mapping reused by later fits.
+struct RingSlab { void* ptr; size_t bytes; int device; bool in_use; };
+static std::mutex g_ring_mu;
+static std::vector<RingSlab> g_ring_slabs;
+static std::map<std::string, void*> g_ring_peers;   // key: device + 64-byte IPC handle
+
+static cudaError_t ring_slab_acquire(size_t bytes, int device, void** out, size_t* got) {
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    for (auto& s : g_ring_slabs)
+        if (!s.in_use && s.device == device && s.bytes >= bytes) {
+            s.in_use = true; *out = s.ptr; *got = s.bytes;
+            return cudaSuccess;
+        }
+    void* q = nullptr;
+    const size_t want = std::max<size_t>(bytes, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return e;
+    g_ring_slabs.push_back(RingSlab{q, want, device, true});
+    *out = q; *got = want;
+    return cudaSuccess;
+}
+static void ring_slab_release(void* q) {
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    for (auto& s : g_ring_slabs)
+        if (s.ptr == q) s.in_use = false;
+}
+static cudaError_t ring_peer_open(const unsigned char* h64, int device, void** out) {
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    std::string key((const char*)h64, 64);
+    key.push_back((char)device);
+    auto it = g_ring_peers.find(key);
+    if (it != g_ring_peers.end()) { *out = it->second; return cudaSuccess; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) g_ring_peers[key] = *out;
+    return e;
+}
+
 static void plan_free(sb2_svd_plan* p) {
     if (!p) return;
     cudaStream_t st = p->alloc_stream;
@@ -1205,11 +1251,9 @@ static void plan_free(sb2_svd_plan* p) {
     free_async(p->yj, st); free_async(p->isq, st); free_async(p->cnt, st); free_async(p->u_ptr, st);
     free_async(p->i_ptr, st); free_async(p->ui_idx, st); free_async(p->iu_idx, st);
     free_async(p->pu, st); free_async(p->qi, st); free_async(p->bu, st); free_async(p->bi, st);
-    if (p->left_ipc && p->left_slab) cudaIpcCloseMemHandle(p->left_slab);
-    if (p->right_ipc && p->right_slab && p->right_slab != p->left_slab) cudaIpcCloseMemHandle(p->right_slab);
-    if (p->slab) {
+    if (p->slab) {   // back to the free list (peer mappings stay open: see ring_slab_acquire)
         cudaStreamSynchronize(st);
-        cudaFree(p->slab);
+        ring_slab_release(p->slab);
     }
     delete p;
 }
@@ -1393,7 +1437,8 @@ int svd_plan_create_dev(int64_t n_users, int64_t n_items, int64_t n, const int32
         PLAN_CUDA(cudaMallocAsync(&p->bi, (size_t)n_items * 4, st));
     } else {
         p->slab_bytes = (2 * p->slab_qi_floats() + 2 * (size_t)p->ni_max + 2 * (size_t)B) * 4;
-        PLAN_CUDA(cudaMalloc(&p->slab, p->slab_bytes));
+        size_t got = 0;
+        PLAN_CUDA(ring_slab_acquire(p->slab_bytes, p->device, &p->slab, &got));
         PLAN_CUDA(cudaMemsetAsync(p->slab, 0, p->slab_bytes, st));
     }
 
@@ -1870,17 +1915,9 @@ int svd_ring_connect_ipc(sb2_svd_plan* p, const unsigned char* left64, const uns
         set_error("svd_ring_connect: not a ring plan (world == 1)");
         return SB2_ERR_INVALID;
     }
-    cudaIpcMemHandle_t h;
-    memcpy(&h, left64, 64);
-    SB2_CUDA(cudaIpcOpenMemHandle(&p->left_slab, h, cudaIpcMemLazyEnablePeerAccess));
-    p->left_ipc = true;
-    if (memcmp(left64, right64, 64) == 0) {  // two ranks: both neighbours are the same slab
-        p->right_slab = p->left_slab;
-    } else {
-        memcpy(&h, right64, 64);
-        SB2_CUDA(cudaIpcOpenMemHandle(&p->right_slab, h, cudaIpcMemLazyEnablePeerAccess));
-    }
-    p->right_ipc = true;
+    SB2_CUDA(ring_peer_open(left64, p->device, &p->left_slab));
+    SB2_CUDA(ring_peer_open(right64, p->device, &p->right_slab));   // two ranks: the same handle, the same mapping
+    p->left_ipc = p->right_ipc = true;
     return SB2_OK;
 }
 // neighbours that live in the same process (one process driving several GPUs, or several ranks of a test sharing
