@@ -1,0 +1,69 @@
+"""profiles/r2_summary.md: the headline table of round 2 from the bench lines (gpurun_out/r2_bench_n*.json, copied to
+profiles/), the predict bench and the ncu summary (profiles/r2_ncu_summary.md, tools/summarize_profiles_r2.py)."""
+import json, os, shutil
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(R, "gpurun_out"), os.path.join(R, "profiles")
+
+
+def line(path):
+    if not os.path.exists(path):
+        return None
+    for ln in open(path):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return None
+
+
+B = {}
+for n in (1, 2, 4, 8):
+    src = os.path.join(G, "r2_bench_n%d.json" % n)
+    if os.path.exists(src):
+        shutil.copyfile(src, os.path.join(P, "r2_bench_n%d.json" % n))
+    B[n] = line(os.path.join(P, "r2_bench_n%d.json" % n))
+for f, dst in (("r2_bench_reference_arm.json", "r2_bench_reference_arm.json"), ("predict.json", "r2_predict.json"),
+               ("sweep_dep.log", "r2_dsgd_dep_sweep.log"), ("sweep_dep2.log", "r2_dsgd_dep_sync_sweep.log")):
+    if os.path.exists(os.path.join(G, f)):
+        shutil.copyfile(os.path.join(G, f), os.path.join(P, dst))
+ref = line(os.path.join(P, "r2_bench_reference_arm.json"))
+pred = json.load(open(os.path.join(P, "r2_predict.json"))) if os.path.exists(os.path.join(P, "r2_predict.json")) else None
+out = ["# Round 2 summary (B200, sm_100a)\n",
+       "Bench lines: r2_bench_n{1,2,4,8}.json (`python bench.py --gpus N --steps 20 --warmup 5`, torchrun for N > 1; the headline",
+       "SVD line + `secondary`: configs[2] / [3] / [4] at their full shapes, sharded over the N ranks), r2_bench_reference_arm.json",
+       "(`--impl reference`), r2_predict.json (tools/bench_predict.py).  ncu evidence of the committed kernels: r2_ncu_summary.md,",
+       "r2_bench_launches.csv, sass_gemm_u8_tc.txt, sass_dsgd_ring.txt.  Experiments: r2_dsgd_dep_*.log.\n",
+       "| N GPUs | SVD c2: ms per fit (resident) | updates/s | roofline frac (HBM, algorithmic bytes) | e2e ms per fit (host arrays) | held-out RMSE (reference 0.889368) | kernel launches per fit |",
+       "|---|---|---|---|---|---|---|"]
+for n, d in B.items():
+    if d:
+        out.append("| %d | %.2f | %.3g | %.3f | %.2f | %.5f | %d |" % (n, d["ms_per_step"], d["value"], d["roofline"]["frac"], d["e2e"]["ms_per_step"],
+                                                                  d["heldout_rmse"], round(d["gpu_launches"] / d["steps"])))
+if ref:
+    out.append("\nReference arm (the compiled reference's Cython `SVD.sgd`, one host core of the same box): %.3g rating-updates/s.\n" % ref["value"])
+out += ["| N GPUs | c3 pearson_baseline build s (default = general path, bit-identical to the reference) | from the host CSR | tensor path (int8 tcgen05) | c3 cosine (default) | c4 SVD++ fit s / RMSE (oracle 0.837962) | c5 NMF 50 epochs s / visits per s / frac of HBM per GPU |",
+        "|---|---|---|---|---|---|---|"]
+for n, d in B.items():
+    if d and d.get("secondary"):
+        s = d["secondary"]
+        out.append("| %d | %.4f | %.4f | %.4f | %.4f | %.4f / %.5f | %.4f / %.3g / %.2f |" % (
+            n, s["c3_pearson_baseline_build_s"], s["c3_pearson_baseline_build_s_from_host_csr"], s["c3_pearson_baseline_build_s_tensor_path"],
+            s["c3_cosine_build_s"], s["c4_svdpp_fit_s"], s["c4_svdpp_heldout_rmse"], s["c5_nmf_epochs_s"], s["c5_nmf_rating_visits_per_s"],
+            s["c5_frac_of_measured_hbm_per_gpu"]))
+d1 = B.get(1)
+if d1:
+    s = d1["secondary"]
+    out += ["", "One GPU, per implementation of config 3 (27k x 138k, 20M half-star ratings, %.3g co-ratings):" % s["c3_co_ratings"], "",
+            "* tensor path: pearson_baseline %.3f s = %.0f TOP/s issued (%.2f of nominal int8 4.5 POP/s), %.0f TOP/s algorithmic; cosine %.3f s = %.0f TOP/s (%.2f)" % (
+                s["c3_pearson_baseline_build_s_tensor_path"], s["c3_tensor_path"]["pearson_baseline_issued_TOPs"],
+                s["c3_tensor_path"]["frac_of_nominal_int8_4500_TOPs_per_gpu"]["pearson_baseline_issued"], s["c3_tensor_path"]["pearson_baseline_algorithmic_TOPs"],
+                s["c3_cosine_build_s_tensor_path"], s["c3_tensor_path"]["cosine_algorithmic_TOPs"], s["c3_tensor_path"]["frac_of_nominal_int8_4500_TOPs_per_gpu"]["cosine_algorithmic"]),
+            "* general path: %.3f s = %.3g co-ratings/s = %.0f GB/s on 76 algorithmic bytes per co-rating = %.2f of the measured HBM peak" % (
+                s["c3_pearson_baseline_build_s_general_path"], s["c3_general_path"]["co_ratings_per_s"], s["c3_general_path"]["achieved_GBs"],
+                s["c3_general_path"]["frac_of_measured_hbm"]),
+            "", "Python API (second call of each, ml-1M shape): " + json.dumps(d1.get("python_api"))]
+if pred:
+    out += ["", "Estimate kernels (ml-1M shape, 2M pairs): k-NN k=40 %.3g pairs/s (KNNBaseline %.3g), %.2f of HBM peak on %.0f B per pair; "
+            "factor model f=100 %.3g pairs/s = %.2f of HBM peak" % (pred["knn_basic"]["pairs_per_s"], pred["knn_baseline"]["pairs_per_s"],
+                                                                    pred["knn_basic"]["frac_of_measured_hbm"], pred["knn_basic"]["algorithmic_bytes_per_pair"],
+                                                                    pred["mf_predict_f100"]["pairs_per_s"], pred["mf_predict_f100"]["frac_of_measured_hbm"])]
+open(os.path.join(P, "r2_summary.md"), "w").write("\n".join(out) + "\n")
+print("\n".join(out))
