@@ -569,6 +569,24 @@ def secondary_metrics(nat, dist, rank, world):
             out["c3_pearson_baseline_build_s_" + tag] = _timed_max(lambda: build("pearson_baseline", inputs=inp, **kw), dist, world, 3)
             out["c3_cosine_build_s_" + tag] = _timed_max(lambda: build("cosine", inputs=inp), dist, world, 3)
         os.environ.pop("SB2_SIM_PATH", None)
+        # a measured int8 tensor peak for the denominators below: cuBLASLt's int8 x int8 -> int32 GEMM (torch._int_mm),
+        # 8192^3, best of 5 -- a library kernel, used as a yardstick only
+        peak_i8 = None
+        try:
+            a8 = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device="cuda")
+            b8 = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device="cuda")
+            torch._int_mm(a8, b8)
+            best = None
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch._int_mm(a8, b8); e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            peak_i8 = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+            del a8, b8
+        except Exception as e:
+            out["c3_int8_peak_error"] = repr(e)
+        out["c3_int8_peak_measured_TOPs_cublaslt_8192"] = peak_i8
         t_pb, t_cos = out["c3_pearson_baseline_build_s_tensor_path"], out["c3_cosine_build_s_tensor_path"]
         # tensor path: issued = 30 digit accumulators over the upper triangle = 15 full n_x^2 n_y contractions, against
         # the G = 2 of the algorithmic count (why the 1e-9 contract needs all 6 + 6 digits of a_y, a_y^2)
@@ -577,7 +595,10 @@ def secondary_metrics(nat, dist, rank, world):
             "cosine_algorithmic_TOPs": ops / t_cos / 1e12,
             "frac_of_nominal_int8_4500_TOPs_per_gpu": {"pearson_baseline_algorithmic": ops / t_pb / 1e12 / (4500.0 * world),
                                                        "pearson_baseline_issued": ops * 7.5 / t_pb / 1e12 / (4500.0 * world),
-                                                       "cosine_algorithmic": ops / t_cos / 1e12 / (4500.0 * world)}}
+                                                       "cosine_algorithmic": ops / t_cos / 1e12 / (4500.0 * world)},
+            "frac_of_measured_int8_cublaslt_per_gpu": None if not peak_i8 else {
+                "pearson_baseline_issued": ops * 7.5 / t_pb / 1e12 / (peak_i8 * world),
+                "cosine_algorithmic": ops / t_cos / 1e12 / (peak_i8 * world)}}
         # general path: per co-rating one 12-byte (x, r) entry read + one 32-byte column record read and written
         t_g = out["c3_pearson_baseline_build_s_general_path"]
         if world == 1:    # (symmetric shards skip the columns before their rows: the count below is the 1-GPU one)
