@@ -510,8 +510,7 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
     const int n_steps = a.n_epochs * n_strata;
     // records + wave table of step j go to buffer (j & 1) with cp.async, issued one step ahead: they land while
     // the previous stratum is being updated instead of costing an L2 round trip at the head of every stratum
-    auto prefetch = [&](int j) {
-        const int s = a.s_begin + j % n_strata;   // stratum within the epoch, [0, P * B)
+    auto prefetch = [&](int j, int s) {   // step j works on stratum s of the epoch, s in [0, P * B)
         const int k0 = coff_s[2 * s];
         const int staged = min(coff_s[2 * s + 1] - k0, a.rec_cap);
         int* rul = rul_s + (size_t)(j & 1) * a.rec_cap;
@@ -529,17 +528,20 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             for (int x = tid; x <= NW; x += nthr) cp_async4(wave + x, wsrc + x);
         }
     };
-    if (n_steps > 0) prefetch(0);
+    if (n_steps > 0) prefetch(0, a.s_begin);
     const int P = a.P;
+    // position of the current step, advanced incrementally at the bottom of the loop (a handful of integer divisions
+    // per stratum are ~0.3k cycles of a 9k-cycle stratum): epoch ep, stratum sg of the epoch, sub-epoch S and local
+    // stratum s (ranks), outer / inner step (T, t), resident super-block D = (Cl + T) % K
+    const int ni_q = a.n_items / B, ni_r = a.n_items - ni_q * B;   // items of block ib (one rank): ni_q + (ib < ni_r)
+    int ep = 0, sg = a.s_begin;
+    int S = P > 1 ? sg / B : 0;
+    int s = sg - S * B;
+    int T = s / C, t = s - T * C;
+    int D = (Cl + T) % K;
     for (int step = 0; step < n_steps; ++step) {
-        const int ep = step / n_strata;
-        const int sg = a.s_begin + (step - ep * n_strata);   // stratum within the epoch, [0, P * B)
-        // ranks: sub-epoch S of the epoch, E sub-epochs since the fit began; launches of a ring cover whole epochs
-        const int S = P > 1 ? sg / B : 0;
-        const int s = sg - S * B;
+        // ranks: E sub-epochs since the fit began; launches of a ring cover whole epochs
         const int E = a.E_base + ep * P + S;
-        const int T = s / C, t = s - T * C;
-        const int D = (Cl + T) % K;
         const int gstep = P > 1 ? E * K + T : ep * n_outer + (T - T_begin);
         const bool first = (sg == a.s_begin) || t == 0;       // of this outer step within the launch
         const bool last = (sg + 1 == a.s_end) || t + 1 == C;
@@ -576,9 +578,9 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             else wait_counter<WAIT_EQ_GPU>(guard, a.flags + ib, gstep);
         }
         __syncthreads();
-        if (step + 1 < n_steps) prefetch(step + 1);
+        if (step + 1 < n_steps) prefetch(step + 1, sg + 1 == a.s_end ? a.s_begin : sg + 1);
         const long long c1 = clock64();
-        const int ni_local = (n_items_sb - ib + B - 1) / B;
+        const int ni_local = P > 1 ? (n_items_sb - ib + B - 1) / B : ni_q + (ib < ni_r ? 1 : 0);
         if (SI && first) {
             const int total = ni_local * F4;
             for (int t0 = tid; t0 < total; t0 += 4 * nthr) {
@@ -761,6 +763,15 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             t_wb += clock64() - c3;
         }
         t_wait += c1 - c0; t_load += c2 - c1; t_upd += c3 - c2;
+        // advance to the next stratum
+        ++sg; ++s; ++t;
+        if (t == C) { t = 0; ++T; D = D + 1 == K ? 0 : D + 1; }
+        if (sg == a.s_end) {            // next epoch of this launch
+            sg = a.s_begin; ++ep;
+            S = P > 1 ? sg / B : 0; s = sg - S * B; T = s / C; t = s - T * C; D = (Cl + T) % K;
+        } else if (s == B) {            // next sub-epoch (rings only: one rank has s_end <= B)
+            s = 0; ++S; T = 0; t = 0; D = Cl % K;
+        }
     }
     if (C > 1) cluster_sync_all();  // no CTA leaves while a neighbour may still address its shared memory
     if (a.prof != nullptr && tid == 0) {
