@@ -156,6 +156,11 @@ __device__ __forceinline__ void mbar_init_cta(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
+// relaxed arrival on a remote mailbox: the caller has already issued ONE fence.acq_rel.cluster that covers both of
+// the hop's arrivals (two release arrivals cost two MEMBARs back to back)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -723,8 +728,9 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
             __syncwarp();
             if ((tid & 31) == 0) {
-                mbar_arrive_remote(left_data_bar + 8u * (n_push & 1));
-                mbar_arrive_remote(right_free_bar + 8u * (n_push & 1));
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                mbar_arrive_remote_relaxed(left_data_bar + 8u * (n_push & 1));
+                mbar_arrive_remote_relaxed(right_free_bar + 8u * (n_push & 1));
             }
             mbar_wait_cluster(guard, &ring_bar[n_push & 1], (n_push >> 1) & 1);
             ++n_push;
