@@ -64,6 +64,7 @@ struct DsgdArgs {
     int n_epochs;
     long long* prof;                    // optional: [CTA][8]: cycles in {ring wait, block load, updates, write-back, group-0 updates}, #group-0 updates, #waves, 0
     int* status;                        // != 0: a wait ran into its deadline (a CTA / a peer rank was never scheduled)
+    int bulk_hop;                       // DSMEM hop as one cp.async.bulk (1) or as per-lane st.shared::cluster (0)
     // ---- ring over P ranks (one process per GPU; P == 1: everything below is unused) --------------------------
     // Rank g owns the users u % P == g for the whole fit and, during sub-epoch E (counted from the start of the
     // fit), the item super-block (g + E) % P, whose (qi, bi) rows live in ring_qi / ring_bi[E & 1].  The CTA that
@@ -180,6 +181,23 @@ __device__ __forceinline__ void mbar_wait_cluster(SpinGuard& g, uint64_t* bar, u
     long long t0 = 0;
     while (!mbar_try_wait_cluster(bar, parity))
         if (g.expired(polls, t0)) return;
+}
+// this CTA's own arrival on one of its mailboxes + the bytes an incoming bulk copy will complete on it
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+// generic-proxy writes to shared memory (the updates of this stratum) become visible to the async proxy (bulk copy)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one asynchronous copy of `bytes` (multiple of 16) from this CTA's shared memory into a neighbour's, completing
+// on the NEIGHBOUR's mailbox (complete_tx): the copy engine moves the block, no thread of this CTA touches it
+__device__ __forceinline__ void dsmem_bulk_push(uint32_t remote_dst, const void* local_src, uint32_t bytes,
+                                                uint32_t remote_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     remote_dst),
+                 "r"((uint32_t)__cvta_generic_to_shared(local_src)), "r"(bytes), "r"(remote_bar)
+                 : "memory");
 }
 __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -461,7 +479,8 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
     // and a single mbarrier cannot tell "one phase ahead" from "not yet" once two phases have completed.
     __shared__ __align__(8) uint64_t ring_bar[4];  // [0,1] data, [2,3] free
     if (tid == 0) {
-        for (int x = 0; x < 4; ++x) mbar_init_cta(&ring_bar[x], (uint32_t)(nthr >> 5));  // one arrival per warp
+        // per-lane hop: one arrival per warp; bulk hop: one arrival per mailbox phase (see the hop below)
+        for (int x = 0; x < 4; ++x) mbar_init_cta(&ring_bar[x], a.bulk_hop ? 1u : (uint32_t)(nthr >> 5));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int nu_local = (a.n_users - ub + B - 1) / B;
@@ -487,7 +506,23 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
     __syncthreads();
     SpinGuard guard{a.status, false};
 
-    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, n_wave = 0, t_hop = 0;
+    long long t_wait = 0, t_load = 0, t_upd = 0, t_wb = 0, n_wave = 0, t_hop = 0, t_free = 0, t_push = 0;
+#ifdef SB2_DSGD_CHECK
+    // debug build (-DSB2_DSGD_CHECK): every rating of a wave stamps its user row and its item row with the wave's
+    // number; a row that already carries the stamp is shared by two ratings of one wave -- a schedule conflict,
+    // reported through status[3] (sb2_svd_plan_status fails).  Rows beyond CHK_ROWS per block are not checked.
+    constexpr int CHK_ROWS = 2048;
+    __shared__ int chk_u[CHK_ROWS], chk_i[CHK_ROWS];
+    for (int x = tid; x < CHK_ROWS; x += nthr) { chk_u[x] = 0; chk_i[x] = 0; }
+    __syncthreads();
+    auto stamp = [&](int ul, int il, bool valid, int tag) {
+        if (valid && gl == 0) {
+            if (ul < CHK_ROWS && atomicExch(&chk_u[ul], tag) == tag) atomicOr(&a.status[3], 1);
+            if (il < CHK_ROWS && atomicExch(&chk_i[il], tag) == tag) atomicOr(&a.status[3], 2);
+            atomicAdd(&a.status[2], 1);   // ratings checked
+        }
+    };
+#endif
 #ifdef SB2_DSGD_WAVE_PROF
     long long t_act = 0, t_bar = 0;  // warp 0: cycles inside the updates of a wave / in the barrier after it
 #endif
@@ -506,10 +541,12 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
     int slot = 0;
     uint32_t n_push = 0;  // pushes done so far (selects the mbarrier phases)
     uint32_t left_data_bar = 0, right_free_bar = 0;  // remote addresses of ring_bar[0] (left) / ring_bar[2] (right)
+    uint32_t right2_free_bar = 0;                    // ring_bar[2] of the CTA two to the right (bulk hop)
     if (C > 1) {
         cluster_sync_all();  // every CTA's mailboxes are initialised before anybody arrives on them
         left_data_bar = dsmem_addr(&ring_bar[0], (uint32_t)(c == 0 ? C - 1 : c - 1));
         right_free_bar = dsmem_addr(&ring_bar[2], (uint32_t)(c + 1 == C ? 0 : c + 1));
+        right2_free_bar = dsmem_addr(&ring_bar[2], (uint32_t)((c + 2) % C));
     }
     const int n_strata = a.s_end - a.s_begin;
     const int n_steps = a.n_epochs * n_strata;
@@ -571,6 +608,9 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
         float* qi_s = ibuf_s + (size_t)slot * a.ibuf;
         float* bi_s = qi_s + (size_t)a.max_il * FP;
         const long long c0 = clock64();
+        // a wait that ran into its deadline anywhere (on this GPU) ends all mailbox traffic of the draining launch:
+        // the word is read here and looked at at the hop, a stratum later
+        const int status_now = ld_relaxed(a.status);
         const int k0 = coff_s[2 * sg], cnt = coff_s[2 * sg + 1] - k0;
         const int staged = min(cnt, a.rec_cap);
         cp_async_wait_all();  // this stratum's records (issued during the previous stratum)
@@ -686,6 +726,18 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
 #endif
                 // a warp whose first lane-group is already past the wave's end holds only dummies: skip it
                 // (warp-uniform test), it would otherwise compete for issue slots with the working warps
+#ifdef SB2_DSGD_CHECK
+                {
+                    const int tag = step * NW + w + 1;
+                    stamp(c_ul, c_il, wb + gid < we, tag);
+                    for (int k = wb + W; k < we; k += W) {
+                        int x_ul, x_il;
+                        float x_r;
+                        fetch(k + gid, k + gid < we, x_ul, x_il, x_r);
+                        stamp(x_ul, x_il, k + gid < we, tag);
+                    }
+                }
+#endif
                 if (wb + gid0 < we) update(c_ul, c_il, c_r, wb + gid < we);
                 for (int k = wb + W; k < we; k += W)
                     if (k + gid0 < we) process(k + gid, k + gid < we);
@@ -714,7 +766,37 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
         }
         }
         const long long c3 = clock64();
-        if (!last) {
+        if (!last && a.bulk_hop) {
+            // fast hop, asynchronous: ONE thread hands the block (a.ibuf floats) to the copy engine, which writes it into
+            // the left neighbour's spare buffer and completes the bytes on the neighbour's data mailbox; no lane
+            // stores, no cluster-scope fence.
+            //   data mailbox  D[k & 1] of push k: this CTA's own arrive.expect_tx + the bytes of the incoming copy
+            //   free mailbox  F[k & 1]: CTA x, once push k has landed in its buffer (so the sender x + 1 no longer needs
+            //     its source buffer), arrives on F[k & 1] of CTA x + 2, the one that writes into x + 1's buffers:
+            //     push k + 1 of x + 2 may overwrite that source.
+            // The source buffer is only read by the copy engine, the working buffer only by this CTA's threads, and a
+            // mailbox is reused every second push, which the free mailbox orders behind the previous use.
+            fence_proxy_async_smem();
+            __syncthreads();
+            const long long c4 = clock64();
+            if (status_now != 0) guard.dead = true;
+            if (tid == 0) {
+                if (n_push > 0) mbar_wait_cluster(guard, &ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
+                const uint32_t bytes = (uint32_t)a.ibuf * 4u;
+                const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
+                if (!guard.dead) {   // a draining launch posts nothing: no transaction count may pile up on a mailbox
+                    mbar_arrive_expect_tx(&ring_bar[n_push & 1], bytes);
+                    dsmem_bulk_push(dst, qi_s, bytes, left_data_bar + 8u * (n_push & 1));
+                }
+            }
+            const long long c5 = clock64();
+            mbar_wait_cluster(guard, &ring_bar[n_push & 1], (n_push >> 1) & 1);
+            if (tid == 0 && !guard.dead) mbar_arrive_remote(right2_free_bar + 8u * (n_push & 1));
+            ++n_push;
+            slot ^= 1;
+            t_free += c4 - c3; t_push += c5 - c4;
+            t_hop += clock64() - c3;
+        } else if (!last) {
             // fast hop (neighbour-to-neighbour, no cluster-wide barrier): once the left neighbour has finished
             // reading its spare buffer (its previous push), copy my block into it through distributed shared
             // memory, tell it the data is there, tell my right neighbour that my block buffer is reusable,
@@ -723,6 +805,7 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             // per warp): no block barrier and no single-thread relay inside the hop.  __syncwarp orders the lanes'
             // remote stores (and their reads of the block being sent) before lane 0's cluster-scope releases.
             if (n_push > 0) mbar_wait_cluster(guard, &ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
+            const long long c4 = clock64();
             const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
             const int n4 = a.ibuf >> 2;
             for (int x = tid; x < n4; x += nthr) dsmem_st4(dst + 16u * x, reinterpret_cast<const float4*>(qi_s)[x]);
@@ -732,6 +815,8 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
                 mbar_arrive_remote_relaxed(left_data_bar + 8u * (n_push & 1));
                 mbar_arrive_remote_relaxed(right_free_bar + 8u * (n_push & 1));
             }
+            const long long c5 = clock64();
+            t_free += c4 - c3; t_push += c5 - c4;
             mbar_wait_cluster(guard, &ring_bar[n_push & 1], (n_push >> 1) & 1);
             ++n_push;
             slot ^= 1;
@@ -782,7 +867,7 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
     if (C > 1) cluster_sync_all();  // no CTA leaves while a neighbour may still address its shared memory
     if (a.prof != nullptr && tid == 0) {
         a.prof[ub * 8 + 0] = t_wait; a.prof[ub * 8 + 1] = t_load; a.prof[ub * 8 + 2] = t_upd; a.prof[ub * 8 + 3] = t_wb;
-        a.prof[ub * 8 + 4] = t_upd; a.prof[ub * 8 + 5] = n_wave; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = t_hop;
+        a.prof[ub * 8 + 4] = t_free; a.prof[ub * 8 + 5] = t_push; a.prof[ub * 8 + 6] = n_wave; a.prof[ub * 8 + 7] = t_hop;
 #ifdef SB2_DSGD_WAVE_PROF
         a.prof[ub * 8 + 4] = t_act; a.prof[ub * 8 + 5] = t_bar;
 #endif
@@ -1673,6 +1758,8 @@ static int fill_args(sb2_svd_plan* p, DsgdArgs& a) {
     if (const char* e = getenv("SB2_DSGD_DEP_SYNC")) a.dep_sync = atoi(e);
     a.ul = p->ul; a.il = p->il; a.r = p->r; a.cell_off = p->off; a.wave_off = p->wave_off; a.rec_cap = p->rec_cap;
     a.pu = p->pu; a.qi = p->qi; a.bu = p->bu; a.bi = p->bi; a.flags = p->flags; a.status = p->status;
+    a.bulk_hop = 1;  // SB2_DSGD_HOP=st: the per-lane st.shared::cluster hop (round 1), for A/B timing
+    if (const char* e = getenv("SB2_DSGD_HOP")) a.bulk_hop = strcmp(e, "st") != 0;
     a.isq = p->isq; a.cnt = p->cnt;
     a.C = p->C; a.ibuf = p->ibuf;
     const sb2_sgd_params& q = p->prm;
@@ -1905,6 +1992,14 @@ int svd_plan_status(sb2_svd_plan* p, cudaStream_t st) {
     int h[4] = {0, 0, 0, 0};
     SB2_CUDA(cudaMemcpyAsync(h, p->status, 16, cudaMemcpyDeviceToHost, st));
     SB2_CUDA(cudaStreamSynchronize(st));
+    if (h[3] != 0) {
+        set_error("dsgd kernel (SB2_DSGD_CHECK build): two ratings of one wave share a %s row",
+                  (h[3] & 1) ? "user" : "item");
+        return SB2_ERR_CUDA;
+    }
+#ifdef SB2_DSGD_CHECK
+    fprintf(stderr, "SB2_DSGD_CHECK: %d rating updates checked, no row shared within a wave\n", h[2]);
+#endif
     if (h[0] != 0) {
         set_error("dsgd kernel: a wait for a neighbour CTA / rank timed out (CTAs not co-resident, or a peer rank "
                   "is not running); the factors of this fit are invalid");

@@ -35,6 +35,9 @@ print("per-CTA cycles (mean over CTAs) wait %.0f load %.0f update %.0f writeback
       % (*m[:4], tot.mean(), np.round(m[:4] / (20 * b.value))))
 print("%.1f waves/stratum; update-phase cycles per wave %.0f; DSMEM hop cycles per stratum %.0f"
       % (m[6] / (20 * b.value), m[2] / max(m[6], 1), m[7] / (20 * b.value)))
-if os.environ.get("WAVE_PROF"):
+if not os.environ.get("WAVE_PROF"):
+    print("of the hop (thread 0): %.0f + %.0f cycles before waiting, %.0f waiting for the right neighbour's block  [SB2_DSGD_HOP=%s]"
+          % (m[4] / (20 * b.value), m[5] / (20 * b.value), (m[7] - m[4] - m[5]) / (20 * b.value), os.environ.get("SB2_DSGD_HOP", "bulk")))
+else:
     print("warp 0 per wave: update path %.0f cycles, barrier %.0f cycles" % (m[4] / max(m[6], 1), m[5] / max(m[6], 1)))
 lib.sb2_svd_plan_destroy(plan)
