@@ -159,6 +159,40 @@ struct KnnSums {
     int ak;
 };
 
+// Bisection on 32-bit VALUES held by the lanes (get(slot, v) -> is this slot a member, and its value): finds the largest
+// member value `cut` with count(v >= cut) >= kk and that count.  Both ends are snapped to member values after every
+// step (lo: the smallest member >= mid, hi: the largest member < mid), so the number of steps is bounded by the number
+// of DISTINCT values in the range (msd / pearson on star ratings produce many equal similarities) as well as by the 32
+// bits.  Needs lo0 / hi0 = the smallest / largest member value and n0 = the number of members (>= kk).
+template <class Get>
+__device__ __forceinline__ void knn_bisect32(int n_slots, int kk, unsigned lo, unsigned hi, int n0, Get get, unsigned& cut,
+                                             int& n_ge) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    cut = lo;
+    n_ge = n0;
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1) + 1;       // lo < mid <= hi
+        int c = 0;
+        unsigned up = 0xFFFFFFFFu, down = 0u;                 // smallest member >= mid, largest member < mid
+        for (int slot = 0; slot < n_slots; ++slot) {
+            unsigned v;
+            if (get(slot, v)) {
+                const bool ge = v >= mid;
+                c += ge;
+                up = (ge && v < up) ? v : up;
+                down = (!ge && v > down) ? v : down;
+            }
+        }
+        c = __reduce_add_sync(FULL, c);
+        if (c >= kk) {
+            lo = __reduce_min_sync(FULL, up); cut = lo; n_ge = c;   // count(>= lo) is still c
+            if (c == kk) break;
+        } else {
+            hi = __reduce_max_sync(FULL, down);                     // >= lo: count(>= lo) >= kk > c
+        }
+    }
+}
+
 template <class TermFn>
 __device__ __forceinline__ KnnSums knn_select_short(const double* __restrict__ srow, const int32_t* __restrict__ idx, int len,
                                                     int k, int lane, unsigned long long* __restrict__ ckey /* [KNN_CAP] */,
@@ -168,73 +202,87 @@ __device__ __forceinline__ KnnSums knn_select_short(const double* __restrict__ s
     const int n_slots = (len + 31) >> 5;   // candidate a = lane + 32 * slot, keys at ckey[slot * 32 + lane]
     // 1. keys of this lane's candidates
     int n_pos = 0;
-    unsigned long long kmax = 0ull, kmin = ~0ull;
-    for (int slot = 0; slot < n_slots; ++slot) {
-        const int a = lane + 32 * slot;
-        unsigned long long key = 0ull;
-        if (a < len) {
-            key = knn_key(srow[idx[a]]);
-            if (key <= KNN_KEY0) key = 0ull;   // sim <= 0 (or NaN): never part of the sums (knns.py:110-113)
+    unsigned hmax = 0u, hmin = 0xFFFFFFFFu;   // high words of the largest / smallest positive key of this lane
+    // eight neighbour indices, then eight gathered similarities, in flight per lane: the gathers are random 8-byte
+    // reads of a sim row (one DRAM / L2 sector each) and the kernel waits on them more than on anything else
+    constexpr int KNN_MLP = 8;
+    for (int slot0 = 0; slot0 < n_slots; slot0 += KNN_MLP) {
+        int ia[KNN_MLP];
+        double sv[KNN_MLP];
+#pragma unroll
+        for (int u = 0; u < KNN_MLP; ++u) {
+            const int a = lane + 32 * (slot0 + u);
+            ia[u] = a < len ? idx[a] : -1;
         }
-        ckey[slot * 32 + lane] = key;
-        if (key) { ++n_pos; kmax = key > kmax ? key : kmax; kmin = key < kmin ? key : kmin; }
+#pragma unroll
+        for (int u = 0; u < KNN_MLP; ++u) sv[u] = ia[u] >= 0 ? srow[ia[u]] : -1.0;
+#pragma unroll
+        for (int u = 0; u < KNN_MLP; ++u) {
+            if (slot0 + u < n_slots) {
+                unsigned long long key = knn_key(sv[u]);
+                if (key <= KNN_KEY0) key = 0ull;   // sim <= 0 (or NaN): never part of the sums (knns.py:110-113)
+                ckey[(slot0 + u) * 32 + lane] = key;
+                if (key) {
+                    const unsigned h = (unsigned)(key >> 32);
+                    ++n_pos; hmax = h > hmax ? h : hmax; hmin = h < hmin ? h : hmin;
+                }
+            }
+        }
     }
     n_pos = __reduce_add_sync(FULL, n_pos);
     KnnSums out{0.0, 0.0, 0};
     if (n_pos == 0) return out;
     const int kk = n_pos < k ? n_pos : k;
-    // 2. cut: the largest T with count(key >= T) >= kk; stop early on a cut with exactly kk candidates above it
+    // 2. cut: the largest candidate key T with count(key >= T) >= kk.  The keys are 64 bits wide but almost always
+    //    differ in their HIGH words (sign, exponent, 20 mantissa bits), or not at all (equal similarities): the
+    //    bisection runs on the high words (32-bit compares and single warp reductions); only when several DIFFERENT keys
+    //    share the high word of the k-th one does a second bisection on the low words of that group follow.
     unsigned long long cut = 1ull;   // n_pos <= k: every positive candidate survives
     int n_ge = n_pos;
+    int n_eq_keep = 0x7FFFFFFF;      // candidates equal to `cut` that survive (in position order)
     if (n_pos > kk) {
-        // warp-wide max / min of the 64-bit keys (two 32-bit reductions each)
-        unsigned h = (unsigned)(kmax >> 32);
-        const unsigned mhi = __reduce_max_sync(FULL, h);
-        const unsigned mlo = __reduce_max_sync(FULL, h == mhi ? (unsigned)kmax : 0u);
-        h = (unsigned)(kmin >> 32);
-        const unsigned nhi = __reduce_min_sync(FULL, h);
-        const unsigned nlo = __reduce_min_sync(FULL, h == nhi ? (unsigned)kmin : 0xFFFFFFFFu);
-        unsigned long long lo = ((unsigned long long)nhi << 32) | nlo;     // count(>= lo) = n_pos >= kk
-        unsigned long long hi = ((unsigned long long)mhi << 32) | mlo;     // count(>= hi + 1) = 0 < kk
-        cut = lo;
-        // Bisection on the key VALUE with both ends snapped to candidate values after every step (lo: the smallest
-        // candidate >= mid, hi: the largest candidate < mid), so the number of steps is bounded by the number of
-        // DISTINCT similarities in the range (msd / pearson on star ratings produce many equal ones) as well as by
-        // the 64 bits of the key.  Invariants: lo and hi are candidate keys, count(>= lo) >= kk, count(> hi) < kk.
-        auto warp_min64 = [&](unsigned long long v) {
-            const unsigned a = __reduce_min_sync(FULL, (unsigned)(v >> 32));
-            const unsigned b2 = __reduce_min_sync(FULL, (unsigned)(v >> 32) == a ? (unsigned)v : 0xFFFFFFFFu);
-            return ((unsigned long long)a << 32) | b2;
-        };
-        auto warp_max64 = [&](unsigned long long v) {
-            const unsigned a = __reduce_max_sync(FULL, (unsigned)(v >> 32));
-            const unsigned b2 = __reduce_max_sync(FULL, (unsigned)(v >> 32) == a ? (unsigned)v : 0u);
-            return ((unsigned long long)a << 32) | b2;
-        };
-        while (lo < hi) {
-            const unsigned long long mid = lo + ((hi - lo) >> 1) + 1;       // lo < mid <= hi
-            int c = 0;
-            unsigned long long up = ~0ull, down = 0ull;   // smallest key >= mid, largest key < mid
+        __syncwarp(FULL);            // the keys of all lanes are in shared memory
+        const unsigned* chi = reinterpret_cast<const unsigned*>(ckey) + 1;   // high word of ckey[j]: chi[2 j]
+        const unsigned lo_h0 = __reduce_min_sync(FULL, hmin), hi_h0 = __reduce_max_sync(FULL, hmax);
+        unsigned cut_h;
+        int n_ge_h;
+        // non-positive candidates have key 0: never >= mid (> lo_h0 > 0), never the largest value below mid
+        knn_bisect32(n_slots, kk, lo_h0, hi_h0, n_pos,
+                     [&](int slot, unsigned& v) { v = chi[2 * (slot * 32 + lane)]; return true; }, cut_h, n_ge_h);
+        if (n_ge_h == kk) {
+            // exactly kk candidates have a high word >= cut_h: they are the survivors, whatever their low words
+            cut = ((unsigned long long)cut_h << 32) - 1ull;
+            n_ge = kk;
+            n_eq_keep = 0;           // (a stray key equal to cut itself has the high word cut_h - 1: not a survivor)
+        } else {
+            // the group with high word cut_h holds the k-th key: how many lie above it, and the range of its low words
+            int c_gt = 0, c_eq = 0;
+            unsigned lmin = 0xFFFFFFFFu, lmax = 0u;
             for (int slot = 0; slot < n_slots; ++slot) {
                 const unsigned long long key = ckey[slot * 32 + lane];
-                const bool ge = key >= mid;
-                c += ge;
-                up = (ge && key < up) ? key : up;
-                down = (!ge && key > down) ? key : down;
+                const unsigned h = (unsigned)(key >> 32), l = (unsigned)key;
+                c_gt += h > cut_h;
+                if (h == cut_h) { ++c_eq; lmin = l < lmin ? l : lmin; lmax = l > lmax ? l : lmax; }
             }
-            c = __reduce_add_sync(FULL, c);
-            if (c >= kk) {
-                lo = warp_min64(up); cut = lo; n_ge = c;   // count(>= lo) is still c
-                if (c == kk) break;
-            } else {
-                hi = warp_max64(down);                      // >= lo: count(>= lo) >= kk > c
-            }
+            c_gt = __reduce_add_sync(FULL, c_gt);
+            c_eq = __reduce_add_sync(FULL, c_eq);
+            lmin = __reduce_min_sync(FULL, lmin);
+            lmax = __reduce_max_sync(FULL, lmax);
+            unsigned cut_l = lmin;
+            int n_ge_l = c_eq;
+            if (lmin != lmax)   // different keys in the group: the (kk - c_gt)-th largest low word
+                knn_bisect32(n_slots, kk - c_gt, lmin, lmax, c_eq,
+                             [&](int slot, unsigned& v) {
+                                 const unsigned long long key = ckey[slot * 32 + lane];
+                                 v = (unsigned)key;
+                                 return (unsigned)(key >> 32) == cut_h;
+                             }, cut_l, n_ge_l);
+            cut = ((unsigned long long)cut_h << 32) | cut_l;
+            n_ge = c_gt + n_ge_l;
         }
-        if (lo >= hi) cut = lo;
     }
     // 3. survivors: key > cut all; key == cut in position order until kk are there (heapq.nlargest keeps list order
     //    among equal keys), i.e. the n_ge - kk LAST candidates equal to `cut` are left out
-    int n_eq_keep = 0x7FFFFFFF;
     if (n_ge > kk) {
         int c_gt = 0;
         for (int slot = 0; slot < n_slots; ++slot) c_gt += ckey[slot * 32 + lane] > cut;

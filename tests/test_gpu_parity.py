@@ -534,6 +534,34 @@ def test_knn_long_lists_and_ties():
         assert np.array_equal(imp, want[2]) and np.array_equal(ak, want[1]) and np.array_equal(est, want[0])
 
 
+def test_knn_threshold_select_on_nearly_equal_similarities():
+    """The short-list select bisects on the high 32 bits of the similarity keys first: similarities that differ only in
+    their low mantissa bits (same high word), exact ties among them, and groups straddling the k-th place must still
+    come out in heapq.nlargest order -- every list length from 1 to a few hundred, several k."""
+    rng = np.random.RandomState(5)
+    n_x = 400
+    lens = np.concatenate([np.arange(1, 70), rng.randint(70, 400, 40)])
+    n_y = len(lens)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = np.concatenate([rng.permutation(n_x)[:ln] for ln in lens]).astype(np.int32)
+    val = rng.randint(1, 6, len(idx)).astype(np.float64)
+    base = np.array([0.5, 0.5, 0.5, 0.25, 0.75, 1.0, 0.1])          # few high words ...
+    sim = base[rng.randint(0, len(base), (n_x, n_x))] + rng.randint(0, 6, (n_x, n_x)) * 2.0 ** -45   # ... many low words, ties
+    sim[rng.rand(n_x, n_x) < 0.05] = -0.3
+    sim[rng.rand(n_x, n_x) < 0.02] = 0.0
+    sim = np.triu(sim) + np.triu(sim, 1).T
+    np.fill_diagonal(sim, 1)
+    x = rng.randint(0, n_x, 4000).astype(np.int32); y = rng.randint(0, n_y, 4000).astype(np.int32)
+    bx = rng.normal(0, 1, n_x); by = rng.normal(0, 1, n_y)
+    for (k, min_k, mode) in ((40, 1, 0), (1, 1, 0), (7, 1, 1), (128, 2, 2), (33, 1, 3)):
+        want = oracle.knn_estimate(x, y, sim, ptr, idx, val, k, min_k, mode, 3.1, bx, by)
+        est = np.empty(len(x)); ak = np.empty(len(x), dtype=np.int32); imp = np.empty(len(x), dtype=np.uint8)
+        nat.check(nat.lib().sb2_knn_predict(len(x), nat.hptr(x), nat.hptr(y), n_x, n_y, nat.hptr(sim), nat.hptr(ptr),
+                                            nat.hptr(idx), nat.hptr(val), k, min_k, mode, 3.1, nat.hptr(bx),
+                                            nat.hptr(by), nat.hptr(est), nat.hptr(ak), nat.hptr(imp)))
+        assert np.array_equal(imp, want[2]) and np.array_equal(ak, want[1]) and np.array_equal(est, want[0])
+
+
 # ---- NMF ------------------------------------------------------------------------------------------------
 def test_u1_nmf_bit_exact(u1, u1_golden, u1_arrays):
     ts, testset = u1
