@@ -299,42 +299,68 @@ __device__ __forceinline__ KnnSums knn_select_short(const double* __restrict__ s
         const unsigned m = __ballot_sync(FULL, take);
         if (take) {
             const int o = base + __popc(m & below);
-            skey[o] = key;
+            skey[o] = key & 0x7FFFFFFFFFFFFFFFull;   // survivors are positive: the similarity's own bits
             spos[o] = lane + 32 * slot;
         }
         base += __popc(m);
         eq_seen += __popc(m_eq);
     }
     __syncwarp(FULL);
-    // rank of every survivor in (key desc, pos asc) -- survivors are in ascending position, so among equal keys the
-    // earlier index wins -- and scatter into sorted order: keys into the (now free) head of ckey, positions into the
-    // second half of spos.  The ranks are a permutation of 0 .. kk-1: no two lanes write the same slot.
-    for (int j0 = 0; j0 < kk; j0 += 64) {   // lane handles survivors j0 + lane and j0 + 32 + lane in one sweep
-        const int ja = j0 + lane, jb = j0 + 32 + lane;
-        const unsigned long long ka = ja < kk ? skey[ja] : 0ull, kb = jb < kk ? skey[jb] : 0ull;
-        int ra = 0, rb = 0;
+    // Rank of every survivor in (sim desc, pos asc) -- survivors are in ascending position, so among equal similarities
+    // the earlier index wins; the ranks are a permutation of 0 .. kk-1.  The lane that ranks a survivor also computes
+    // its term of the weighted sum and drops (sim, term) at its rank into bt[] (the candidate keys are dead by now).
+    // Survivors are positive, so their similarities compare as doubles (one DSETP instead of a two-word integer compare).
+    double2* bt = reinterpret_cast<double2*>(ckey);
+    const double* ssim = reinterpret_cast<const double*>(skey);
+    auto place = [&](int j, int rank, double sj) { bt[rank] = make_double2(sj, term_of(sj, spos[j])); };
+    if (kk <= 48) {
+        // lane -> survivor `lane` against all kk; survivors 32 .. kk-1 (k = 40, the reference's default: eight of them)
+        // are ranked by `parts` lanes each, every one counting a slice of the survivors
+        const int ja = lane;
+        const double sa = ja < kk ? ssim[ja] : 0.0;
+        int ra = 0;
         for (int t = 0; t < kk; ++t) {
-            const unsigned long long kt = skey[t];
-            ra += (kt > ka) || (kt == ka && t < ja);
-            rb += (kt > kb) || (kt == kb && t < jb);
+            const double st = ssim[t];
+            ra += (st > sa) || (st == sa && t < ja);
         }
-        if (ja < kk) { ckey[ra] = ka; spos[KNN_KCAP + ra] = spos[ja]; }
-        if (jb < kk) { ckey[rb] = kb; spos[KNN_KCAP + rb] = spos[jb]; }
+        if (ja < kk) place(ja, ra, sa);
+        if (kk > 32) {
+            const int per = kk <= 40 ? 8 : 16, parts = 32 / per;
+            const int jb = 32 + (lane % per), q = lane / per;
+            const double sb = jb < kk ? ssim[jb] : 0.0;
+            const int chunk = (kk + parts - 1) / parts, t0 = q * chunk;
+            int rb = 0;
+            for (int i = 0; i < chunk; ++i) {
+                const int t = t0 + i;
+                if (t < kk) {
+                    const double st = ssim[t];
+                    rb += (st > sb) || (st == sb && t < jb);
+                }
+            }
+            for (int o = per; o < 32; o <<= 1) rb += __shfl_xor_sync(FULL, rb, o);
+            if (q == 0 && jb < kk) place(jb, rb, sb);
+        }
+    } else {
+        for (int j0 = 0; j0 < kk; j0 += 64) {   // lane handles survivors j0 + lane and j0 + 32 + lane in one sweep
+            const int ja = j0 + lane, jb = j0 + 32 + lane;
+            const double sa = ja < kk ? ssim[ja] : 0.0, sb = jb < kk ? ssim[jb] : 0.0;
+            int ra = 0, rb = 0;
+            for (int t = 0; t < kk; ++t) {
+                const double st = ssim[t];
+                ra += (st > sa) || (st == sa && t < ja);
+                rb += (st > sb) || (st == sb && t < jb);
+            }
+            if (ja < kk) place(ja, ra, sa);
+            if (jb < kk) place(jb, rb, sb);
+        }
     }
     __syncwarp(FULL);
-    // ordered sums: one neighbour per lane computes its term, then every lane folds the batch in order
-    for (int j0 = 0; j0 < kk; j0 += 32) {
-        const int j = j0 + lane;
-        double bs = 0.0, term = 0.0;
-        if (j < kk) {
-            bs = knn_unkey(ckey[j]);
-            term = term_of(bs, spos[KNN_KCAP + j]);
-        }
-        const int nb = kk - j0 < 32 ? kk - j0 : 32;
-        for (int t = 0; t < nb; ++t) {
-            out.sum_sim = __dadd_rn(out.sum_sim, __shfl_sync(FULL, bs, t));
-            out.sum_r = __dadd_rn(out.sum_r, __shfl_sync(FULL, term, t));
-        }
+    // ordered sums: every lane folds the kk (sim, term) pairs in selection order (one 16-byte broadcast read each)
+#pragma unroll 4
+    for (int t = 0; t < kk; ++t) {
+        const double2 v = bt[t];
+        out.sum_sim = __dadd_rn(out.sum_sim, v.x);
+        out.sum_r = __dadd_rn(out.sum_r, v.y);
     }
     out.ak = kk;
     __syncwarp(FULL);   // the buffers are reused by this warp's next pair
@@ -425,7 +451,7 @@ knn_predict_kernel(int64_t n_pairs, const int32_t* __restrict__ x, const int32_t
     // long-list path: sorted lane buffers [KNN_L][32] of keys / positions.  Short-list path: candidate keys
     // [KNN_SLOTS][32] (their head is reused for the sorted survivor keys), survivor keys, survivor positions
     // (first half: in position order, second half: sorted)
-    __shared__ unsigned long long bkey_s[KNN_WARPS][KNN_CAP];
+    __shared__ __align__(16) unsigned long long bkey_s[KNN_WARPS][KNN_CAP];
     __shared__ int bpos_s[KNN_WARPS][KNN_L * 32 > 2 * KNN_KCAP ? KNN_L * 32 : 2 * KNN_KCAP];
     __shared__ unsigned long long skey_s[KNN_WARPS][KNN_KCAP];
     static_assert(KNN_KCAP <= KNN_CAP && KNN_L * 32 <= KNN_CAP, "buffer reuse");
