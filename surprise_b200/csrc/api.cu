@@ -271,11 +271,9 @@ int sb2_baseline_sgd(int64_t n_users, int64_t n_items, int64_t n, const int32_t*
 }
 
 // ---- SVD / SVD++ -------------------------------------------------------------------------------
-static int svd_like_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
-                            const double* r, const int64_t* u_ptr, const int32_t* ui_idx, const sb2_sgd_params* prm,
-                            double* pu, double* qi, double* yj, double* bu, double* bi, cudaStream_t st) {
-    sb2_svd_plan* plan = nullptr;
-    SB2_TRY(svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, yj != nullptr, u_ptr, ui_idx, 0, 1, st, &plan));
+// reset -> run -> read -> status on an existing plan; destroys the plan
+static int svd_like_run_plan(sb2_svd_plan* plan, const sb2_sgd_params* prm, double* pu, double* qi, double* yj, double* bu,
+                             double* bi, cudaStream_t st) {
     int rc = svd_plan_reset_dev(plan, pu, qi, yj, st);
     if (rc == SB2_OK) rc = svd_plan_run(plan, prm->n_epochs, st);
     if (rc == SB2_OK) rc = svd_plan_read_dev(plan, pu, qi, bu, bi, yj, st);
@@ -286,6 +284,14 @@ static int svd_like_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const i
     }
     svd_plan_destroy(plan);
     return rc;
+}
+
+static int svd_like_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i,
+                            const double* r, const int64_t* u_ptr, const int32_t* ui_idx, const sb2_sgd_params* prm,
+                            double* pu, double* qi, double* yj, double* bu, double* bi, cudaStream_t st) {
+    sb2_svd_plan* plan = nullptr;
+    SB2_TRY(svd_plan_create_dev(n_users, n_items, n, u, i, r, prm, yj != nullptr, u_ptr, ui_idx, 0, 1, st, &plan));
+    return svd_like_run_plan(plan, prm, pu, qi, yj, bu, bi, st);
 }
 
 int sb2_svd_fit_dev(int64_t n_users, int64_t n_items, int64_t n, const int32_t* u, const int32_t* i, const double* r,
@@ -317,19 +323,48 @@ static int svd_like_fit_host(int64_t n_users, int64_t n_items, int64_t n, const 
     SB2_TRY(upload(d_u, u, (size_t)n, st));
     SB2_TRY(upload(d_i, i, (size_t)n, st));
     SB2_TRY(upload(d_r, r, (size_t)n, st));
-    SB2_TRY(upload(d_pu, pu, (size_t)n_users * f, st));
-    SB2_TRY(upload(d_qi, qi, (size_t)n_items * f, st));
     if (yj) {
         SB2_TRY(upload(d_up, u_ptr, (size_t)n_users + 1, st));
         SB2_TRY(upload(d_ui, ui_idx, (size_t)n, st));
-        SB2_TRY(upload(d_yj, yj, (size_t)n_items * f, st));
     }
+    // The initial factors are not needed before the plan exists: they travel on a second stream while the ratings
+    // are stratified and coloured (plan creation: ~0.1 ms of kernels + one status read-back at the ml-1M shape)
+    struct Side { cudaStream_t s = nullptr; cudaEvent_t alloc = nullptr, up = nullptr; };
+    static Side sides[64];   // one per device, created on first use (the host forms are not re-entrant per device)
+    int dev = 0;
+    SB2_CUDA(cudaGetDevice(&dev));
+    Side& sd = sides[dev & 63];
+    if (!sd.s) {
+        SB2_CUDA(cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking));
+        SB2_CUDA(cudaEventCreateWithFlags(&sd.alloc, cudaEventDisableTiming));
+        SB2_CUDA(cudaEventCreateWithFlags(&sd.up, cudaEventDisableTiming));
+    }
+    cudaStream_t side = sd.s;
+    cudaEvent_t ev_alloc = sd.alloc, ev_up = sd.up;
+    SB2_TRY(d_pu.alloc((size_t)n_users * f * 8 + 16, st));
+    SB2_TRY(d_qi.alloc((size_t)n_items * f * 8 + 16, st));
+    if (yj) SB2_TRY(d_yj.alloc((size_t)n_items * f * 8 + 16, st));
     SB2_TRY(d_bu.alloc((size_t)n_users * 8, st));
     SB2_TRY(d_bi.alloc((size_t)n_items * 8, st));
-    SB2_TRY(svd_like_fit_dev(n_users, n_items, n, d_u.as<int32_t>(), d_i.as<int32_t>(), d_r.as<double>(),
-                             yj ? d_up.as<int64_t>() : nullptr, yj ? d_ui.as<int32_t>() : nullptr, prm,
-                             d_pu.as<double>(), d_qi.as<double>(), yj ? d_yj.as<double>() : nullptr, d_bu.as<double>(),
-                             d_bi.as<double>(), st));
+    SB2_CUDA(cudaEventRecord(ev_alloc, st));
+    SB2_CUDA(cudaStreamWaitEvent(side, ev_alloc, 0));   // stream-ordered allocations: usable on `side` from here on
+    SB2_CUDA(cudaMemcpyAsync(d_pu.p, pu, (size_t)n_users * f * 8, cudaMemcpyHostToDevice, side));
+    SB2_CUDA(cudaMemcpyAsync(d_qi.p, qi, (size_t)n_items * f * 8, cudaMemcpyHostToDevice, side));
+    if (yj) SB2_CUDA(cudaMemcpyAsync(d_yj.p, yj, (size_t)n_items * f * 8, cudaMemcpyHostToDevice, side));
+    SB2_CUDA(cudaEventRecord(ev_up, side));
+    sb2_svd_plan* plan = nullptr;
+    int rc = svd_plan_create_dev(n_users, n_items, n, d_u.as<int32_t>(), d_i.as<int32_t>(), d_r.as<double>(), prm,
+                                 yj != nullptr, yj ? d_up.as<int64_t>() : nullptr, yj ? d_ui.as<int32_t>() : nullptr, 0, 1,
+                                 st, &plan);
+    cudaError_t we = cudaStreamWaitEvent(st, ev_up, 0);
+    if (rc != SB2_OK || we != cudaSuccess) {
+        cudaStreamSynchronize(side);   // the buffers are freed on `st` when this function returns
+        if (plan) svd_plan_destroy(plan);
+        if (rc == SB2_OK) { set_error("svd_fit: cudaStreamWaitEvent failed: %s", cudaGetErrorString(we)); rc = SB2_ERR_CUDA; }
+        return rc;
+    }
+    SB2_TRY(svd_like_run_plan(plan, prm, d_pu.as<double>(), d_qi.as<double>(), yj ? d_yj.as<double>() : nullptr,
+                              d_bu.as<double>(), d_bi.as<double>(), st));
     SB2_TRY(download(pu, d_pu.p, (size_t)n_users * f, st));
     SB2_TRY(download(qi, d_qi.p, (size_t)n_items * f, st));
     if (yj) SB2_TRY(download(yj, d_yj.p, (size_t)n_items * f, st));

@@ -947,6 +947,7 @@ __global__ void dsgd_key_kernel(int64_t n, const int32_t* __restrict__ u, const 
 // user row / item row that precede it in the colour-sorted order.  A proper colour occurs at most once per row, so
 // that is a popcount of the row's final mask below the record's colour; tail records (several per row possible)
 // follow all coloured ones in placement order.
+constexpr int COLOR_CAP = 512;  // ratings of a cell staged in shared memory at a time
 __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int P, int max_ul, int max_il,
                                                         const int* __restrict__ cell_off, const int* __restrict__ val,
                                                         const int32_t* __restrict__ u, const int32_t* __restrict__ i,
@@ -957,54 +958,92 @@ __global__ void __launch_bounds__(32) dsgd_color_kernel(int n_cells, int B, int 
     extern __shared__ unsigned long long masks[];  // [max_ul] user masks, [max_il] item masks, then int tail counters
     int* tail_cnt = reinterpret_cast<int*>(masks + max_ul + max_il);
     __shared__ int hist[NW + 1];
+    // the greedy colouring is sequential (lane 0), everything around it is not: the 32 lanes fetch a chunk of the
+    // cell's ratings (three dependent global reads each: position -> (u, i) -> local rows) into shared memory, lane 0
+    // colours / places the chunk out of shared memory, the 32 lanes write the results
+    __shared__ int s_src[COLOR_CAP], s_ul[COLOR_CAP], s_il[COLOR_CAP], s_pos[COLOR_CAP], s_dep[COLOR_CAP];
+    __shared__ uint8_t s_col[COLOR_CAP];
     const int lane = threadIdx.x;
     for (int cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const int k0 = cell_off[cell], k1 = cell_off[cell + 1];
         for (int t = lane; t < max_ul + max_il; t += 32) { masks[t] = 0ull; tail_cnt[t] = 0; }
         for (int t = lane; t <= NW; t += 32) hist[t] = 0;
+        if (lane == 0) atomicMax(&status[1], k1 - k0);
         __syncwarp();
-        if (lane == 0) {
-            atomicMax(&status[1], k1 - k0);
-            for (int k = k0; k < k1; ++k) {
-                const int src = val[k];
-                const int ul = (u[src] / P) / B, il = (i[src] / P) / B;
-                const unsigned long long used = masks[ul] | masks[max_ul + il];
-                int c = __ffsll((long long)~used) - 1;  // lowest free colour, -1 if none
-                if (c < 0 || c >= NW - 1) c = NW - 1;
-                else {
-                    masks[ul] |= 1ull << c;
-                    masks[max_ul + il] |= 1ull << c;
-                }
-                color_tmp[k] = (uint8_t)c;
-                hist[c + 1]++;
+        auto stage = [&](int c0, int n, bool with_colour) {
+            for (int t = lane; t < n; t += 32) {
+                const int src = val[c0 + t];
+                s_src[t] = src;
+                s_ul[t] = (u[src] / P) / B;
+                s_il[t] = (i[src] / P) / B;
+                if (with_colour) s_col[t] = color_tmp[c0 + t];
             }
-            for (int c = 0; c < NW; ++c) hist[c + 1] += hist[c];
-            for (int c = 0; c <= NW; ++c) wave_off[(size_t)cell * (NW + 1) + c] = hist[c];
-            int worst = 0;
-            for (int k = k0; k < k1; ++k) {
-                const int src = val[k];
-                const int c = color_tmp[k];
-                const int pos = k0 + hist[c]++;
-                const int ul = (u[src] / P) / B, il = (i[src] / P) / B;
-                ul_out[pos] = ul;
-                il_out[pos] = il;
-                r_out[pos] = (float)r[src];
-                if (dep_out != nullptr) {
-                    int nu, nv;
-                    if (c < NW - 1) {
-                        const unsigned long long below = (1ull << c) - 1ull;
-                        nu = __popcll(masks[ul] & below);
-                        nv = __popcll(masks[max_ul + il] & below);
-                    } else {
-                        nu = __popcll(masks[ul]) + tail_cnt[ul]++;
-                        nv = __popcll(masks[max_ul + il]) + tail_cnt[max_ul + il]++;
+            __syncwarp();
+        };
+        // pass 1: colours in the cell's (stable) input order
+        for (int c0 = k0; c0 < k1; c0 += COLOR_CAP) {
+            const int n = min(COLOR_CAP, k1 - c0);
+            stage(c0, n, false);
+            if (lane == 0) {
+                for (int t = 0; t < n; ++t) {
+                    const int ul = s_ul[t], il = s_il[t];
+                    const unsigned long long used = masks[ul] | masks[max_ul + il];
+                    int c = __ffsll((long long)~used) - 1;  // lowest free colour, -1 if none
+                    if (c < 0 || c >= NW - 1) c = NW - 1;
+                    else {
+                        masks[ul] |= 1ull << c;
+                        masks[max_ul + il] |= 1ull << c;
                     }
-                    worst = max(worst, max(nu, nv));
-                    dep_out[pos] = (nu & 0xFFFF) | (nv << 16);
+                    s_col[t] = (uint8_t)c;
+                    hist[c + 1]++;
                 }
             }
-            if (dep_out != nullptr) atomicMax(&status[2], worst);
+            __syncwarp();
+            if (k1 - k0 > COLOR_CAP)   // a single chunk stays in shared memory for pass 2
+                for (int t = lane; t < n; t += 32) color_tmp[c0 + t] = s_col[t];
+            __syncwarp();
         }
+        if (lane == 0)
+            for (int c = 0; c < NW; ++c) hist[c + 1] += hist[c];
+        __syncwarp();
+        for (int c = lane; c <= NW; c += 32) wave_off[(size_t)cell * (NW + 1) + c] = hist[c];
+        __syncwarp();
+        // pass 2: counting sort by colour (stable), dependency counts for the DEP kernels
+        int worst = 0;
+        for (int c0 = k0; c0 < k1; c0 += COLOR_CAP) {
+            const int n = min(COLOR_CAP, k1 - c0);
+            if (k1 - k0 > COLOR_CAP) stage(c0, n, true);
+            if (lane == 0) {
+                for (int t = 0; t < n; ++t) {
+                    const int c = s_col[t];
+                    s_pos[t] = k0 + hist[c]++;
+                    if (dep_out != nullptr) {
+                        const int ul = s_ul[t], il = s_il[t];
+                        int nu, nv;
+                        if (c < NW - 1) {
+                            const unsigned long long below = (1ull << c) - 1ull;
+                            nu = __popcll(masks[ul] & below);
+                            nv = __popcll(masks[max_ul + il] & below);
+                        } else {
+                            nu = __popcll(masks[ul]) + tail_cnt[ul]++;
+                            nv = __popcll(masks[max_ul + il]) + tail_cnt[max_ul + il]++;
+                        }
+                        worst = max(worst, max(nu, nv));
+                        s_dep[t] = (nu & 0xFFFF) | (nv << 16);
+                    }
+                }
+            }
+            __syncwarp();
+            for (int t = lane; t < n; t += 32) {
+                const int pos = s_pos[t];
+                ul_out[pos] = s_ul[t];
+                il_out[pos] = s_il[t];
+                r_out[pos] = (float)r[s_src[t]];
+                if (dep_out != nullptr) dep_out[pos] = s_dep[t];
+            }
+            __syncwarp();
+        }
+        if (dep_out != nullptr && lane == 0) atomicMax(&status[2], worst);
         __syncwarp();
     }
 }
