@@ -175,6 +175,29 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+// CTA-scope wait (the default semantics): all that TMA-style consumers need -- the bytes a bulk copy completes on the
+// mailbox are visible to the waiting CTA once the phase completes.  No L1 invalidation (CCTL.IVALL) as after a
+// cluster-scope acquire.
+__device__ __forceinline__ bool mbar_try_wait_cta(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cta(SpinGuard& g, uint64_t* bar, uint32_t parity) {
+    if (g.dead) return;
+    unsigned polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait_cta(bar, parity))
+        if (g.expired(polls, t0)) return;
+}
 __device__ __forceinline__ void mbar_wait_cluster(SpinGuard& g, uint64_t* bar, uint32_t parity) {
     if (g.dead) return;
     unsigned polls = 0;
@@ -773,7 +796,10 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             //   data mailbox  D[k & 1] of push k: this CTA's own arrive.expect_tx + the bytes of the incoming copy
             //   free mailbox  F[k & 1]: CTA x, once push k has landed in its buffer (so the sender x + 1 no longer needs
             //     its source buffer), arrives on F[k & 1] of CTA x + 2, the one that writes into x + 1's buffers:
-            //     push k + 1 of x + 2 may overwrite that source.
+            //     push k + 1 of x + 2 may overwrite that source.  The arrival publishes no data of this CTA (the copy
+            //     engine's reads of the source are over when its bytes have landed): relaxed, and the waits are
+            //     CTA-scope -- a release / acquire pair at cluster scope costs a MEMBAR.ALL.GPU and an L1 invalidation
+            //     per stratum on the path of the thread every other warp then waits for.
             // The source buffer is only read by the copy engine, the working buffer only by this CTA's threads, and a
             // mailbox is reused every second push, which the free mailbox orders behind the previous use.
             fence_proxy_async_smem();
@@ -781,7 +807,7 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
             const long long c4 = clock64();
             if (status_now != 0) guard.dead = true;
             if (tid == 0) {
-                if (n_push > 0) mbar_wait_cluster(guard, &ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
+                if (n_push > 0) mbar_wait_cta(guard, &ring_bar[2 + ((n_push - 1) & 1)], ((n_push - 1) >> 1) & 1);
                 const uint32_t bytes = (uint32_t)a.ibuf * 4u;
                 const uint32_t dst = dsmem_addr(ibuf_s + (size_t)(slot ^ 1) * a.ibuf, (uint32_t)(c == 0 ? C - 1 : c - 1));
                 if (!guard.dead) {   // a draining launch posts nothing: no transaction count may pile up on a mailbox
@@ -790,8 +816,8 @@ __device__ __forceinline__ void dsgd_body(const DsgdArgs& a, const int ub) {
                 }
             }
             const long long c5 = clock64();
-            mbar_wait_cluster(guard, &ring_bar[n_push & 1], (n_push >> 1) & 1);
-            if (tid == 0 && !guard.dead) mbar_arrive_remote(right2_free_bar + 8u * (n_push & 1));
+            mbar_wait_cta(guard, &ring_bar[n_push & 1], (n_push >> 1) & 1);
+            if (tid == 0 && !guard.dead) mbar_arrive_remote_relaxed(right2_free_bar + 8u * (n_push & 1));
             ++n_push;
             slot ^= 1;
             t_free += c4 - c3; t_push += c5 - c4;
