@@ -38,6 +38,9 @@ for n, d in B.items():
         out.append("| %d | %.2f | %.3g | %.3f | %.2f | %.5f | %d |" % (n, d["ms_per_step"], d["value"], d["roofline"]["frac"], d["e2e"]["ms_per_step"],
                                                                   d["heldout_rmse"], round(d["gpu_launches"] / d["steps"])))
 if ref:
+    out.append("\nThe N = 4 and N = 8 lines were measured one commit before the last change to the hop's mailbox semantics (CTA-scope "
+               "waits, relaxed free-arrival: -0.9 ms per fit at N = 1 and N = 2); the GPU budget of the round did not allow re-running "
+               "them.  The driver's SCALE run has all four N on the final kernel.\n")
     out.append("\nReference arm (the compiled reference's Cython `SVD.sgd`, one host core of the same box): %.3g rating-updates/s.\n" % ref["value"])
 out += ["| N GPUs | c3 pearson_baseline build s (default = general path, bit-identical to the reference) | from the host CSR | tensor path (int8 tcgen05) | c3 cosine (default) | c4 SVD++ fit s / RMSE (oracle 0.837962) | c5 NMF 50 epochs s / visits per s / frac of HBM per GPU |",
         "|---|---|---|---|---|---|---|"]
